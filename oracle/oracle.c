@@ -1,0 +1,271 @@
+/* oracle/oracle.c -- TEST INFRASTRUCTURE.  CPU restatement of MMseqs2's alignment hot path.
+ *
+ * This file is the checker, never the product: only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load liboracle.so.  Nothing under
+ * mmseqs2_b200/ links, imports or executes it.
+ *
+ * Parity status: PINNED.  Every function below is checked against the reference's own code
+ * compiled in place from /root/reference (oracle/_ref/libmmseqs_ref.so, see oracle/Makefile and
+ * oracle/ref_glue.cpp) by tests/test_oracle_vs_ref.py, and against the committed fixtures in
+ * tests/golden/ (generated from that library by tests/golden/make_golden.py).
+ * Exception: word-mode start positions in the *official* binary come from the Rust
+ * block-aligner, which cannot be built here; they are pinned against the reference's own
+ * fallback path (StripedSmithWaterman.cpp:879-882) only.
+ *
+ * Conventions: residues are numeric codes 0..A-1; `mat` is the A*A int16 substitution matrix
+ * (row-major, mat[a*A+b] = BaseMatrix::subMatrix[a][b]); `cb` is the int8 composition bias per
+ * query position (all zero when the correction is off).  Plain scalar C, textbook recurrences:
+ * SURVEY.md T1-T5 establish (and tests/test_oracle_vs_ref.py re-checks) that SIMD width and
+ * striping do not leak into any output.
+ */
+#include <stddef.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_MAX(a, b) ((a) > (b) ? (a) : (b))
+#define ORC_MIN(a, b) ((a) < (b) ? (a) : (b))
+
+/* ------------------------------------------------------------------------------------------
+ * Composition bias, float.  Follows SubstitutionMatrix::calcLocalAaBiasCorrection,
+ * src/commons/SubstitutionMatrix.cpp:79-109 -- the float/double mixing is part of the contract.
+ * ------------------------------------------------------------------------------------------ */
+void orc_comp_bias(const int16_t *mat, const double *pback, int A, const uint8_t *seq, int N, float scale,
+                   float *out) {
+    const int windowSize = 40;
+    for (int i = 0; i < N; i++) {
+        const int minPos = ORC_MAX(0, i - windowSize / 2);
+        const int maxPos = ORC_MIN(N, i + windowSize / 2);
+        const int windowLength = maxPos - minPos;
+        int sumSubScores = 0;
+        const int16_t *row = mat + (size_t) seq[i] * A;
+        for (int j = minPos; j < maxPos; j++) sumSubScores += row[seq[j]];
+        sumSubScores -= row[seq[i]];
+        float deltaS_i = (float) sumSubScores;
+        deltaS_i = (float) ((double) deltaS_i / (-1.0 * (double) (float) windowLength));
+        for (int a = 0; a < A; a++) deltaS_i = (float) ((double) deltaS_i + pback[a] * (double) (float) row[a]);
+        out[i] = scale * deltaS_i;
+    }
+}
+
+/* int8 rounding used by the gapped/ungapped-scan profile: StripedSmithWaterman.cpp:1379
+ * ((int8_t) binds to the comparison, the float is then converted on assignment). */
+void orc_round_bias_ssw(const float *in, int N, int8_t *out) {
+    for (int i = 0; i < N; i++) {
+        double v = (in[i] < 0.0) ? (in[i] - 0.5) : (in[i] + 0.5); /* float -/+ double literal: double */
+        out[i] = (int8_t) v;
+    }
+}
+
+/* int8 rounding used by the per-diagonal scorer (note the /4): UngappedAlignment.cpp:395-400 */
+void orc_round_bias_diag(const float *in, int N, int8_t *out) {
+    for (int i = 0; i < N; i++) {
+        float v = in[i];
+        v = (v < 0.0) ? (float) (v / 4 - 0.5) : (float) (v / 4 + 0.5);
+        out[i] = (int8_t) (char) v;
+    }
+}
+
+/* Profile bias constant: StripedSmithWaterman.cpp:1375-1406.  cbEnabled = aaBiasCorrection flag. */
+int orc_ssw_bias(const int16_t *mat, int A, const int8_t *cb, int qL, int cbEnabled) {
+    int bias = 0;
+    for (int i = 0; i < A * A; i++) {
+        int8_t m = (int8_t) mat[i];
+        if (m < bias) bias = m;
+    }
+    int compositionBias = 0;
+    if (cbEnabled) {
+        for (int i = 0; i < qL; i++) compositionBias = (compositionBias < cb[i]) ? compositionBias : cb[i];
+        compositionBias = ORC_MIN(compositionBias, 0);
+    }
+    return abs(bias) + abs(compositionBias);
+}
+
+/* score of query position j against target residue t: mat[t][q[j]] + cb[j]
+ * (createQueryProfile, StripedSmithWaterman.cpp:753-786: row index is the TARGET residue). */
+static inline int orc_s(const int16_t *mat, int A, const uint8_t *q, const int8_t *cb, int j, int t) {
+    return mat[(size_t) t * A + q[j]] + cb[j];
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A2: SmithWaterman::ungapped_alignment, StripedSmithWaterman.cpp:1817-1876.
+ * Saturating u8: S(j,i) = subs_u8(adds_u8(S(j-1,i-1), s+bias), bias).
+ * ------------------------------------------------------------------------------------------ */
+int orc_ungapped_alignment(const int16_t *mat, int A, const uint8_t *q, int qL, const int8_t *cb, int bias,
+                           const uint8_t *t, int tL) {
+    int *prev = (int *) calloc((size_t) qL + 1, sizeof(int));
+    int *cur = (int *) calloc((size_t) qL + 1, sizeof(int));
+    int best = 0;
+    for (int i = 0; i < tL; i++) {
+        for (int j = 0; j < qL; j++) {
+            int diag = (j == 0) ? 0 : prev[j - 1];
+            int p = (uint8_t) (int8_t) (orc_s(mat, A, q, cb, j, t[i]) + bias); /* profile byte as stored */
+            int v = diag + p;
+            if (v > 255) v = 255;
+            v -= bias;
+            if (v < 0) v = 0;
+            cur[j] = v;
+            if (v > best) best = v;
+        }
+        int *tmp = prev; prev = cur; cur = tmp;
+    }
+    free(prev); free(cur);
+    return best;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A3/A4: one direction of the affine local DP with the reference's reporting rules.
+ * sw_sse2_byte StripedSmithWaterman.cpp:98-299, sw_sse2_word :301-476 (H,E,F recurrences and
+ * the "first column where the running max strictly increases" end rule :233-247 / :414-424,
+ * smallest query index in the saved column :263-271 / :441-449).
+ *
+ * qs/ts with strides let the same routine run forward (stride +1) or on reversed prefixes
+ * (stride -1), which is how alignStartPosBacktrace (:1129-1183) reuses the kernels.
+ * terminate < 0: scan everything.  terminate >= 0: stop at the first column whose max equals it.
+ * Returns max; *endCol = column (scan order) of the saved column or -1; *endRow = smallest row
+ * with H == max in the saved column (rows >= 0), or defaultRow when nothing was saved.
+ * ------------------------------------------------------------------------------------------ */
+static int orc_gotoh(const int16_t *mat, int A, const uint8_t *q, const int8_t *cb, int qL, int qStride,
+                     const uint8_t *t, int tL, int tStride, int go, int ge, int terminate, int *endCol,
+                     int *endRow) {
+    int *H = (int *) calloc((size_t) qL + 1, sizeof(int));   /* H[j+1] = H(prev col, row j) */
+    int *E = (int *) calloc((size_t) qL + 1, sizeof(int));
+    int *saved = (int *) calloc((size_t) qL + 1, sizeof(int));
+    int max = 0, ec = -1;
+    for (int i = 0; i < tL; i++) {
+        int tr = t[(ptrdiff_t) i * tStride];
+        int diag = 0, F = 0, colmax = 0;
+        for (int j = 0; j < qL; j++) {
+            int s = mat[(size_t) tr * A + q[(ptrdiff_t) j * qStride]] + cb[(ptrdiff_t) j * qStride];
+            int h = diag + s;
+            int e = E[j + 1];
+            if (h < e) h = e;
+            if (h < F) h = F;
+            if (h < 0) h = 0;
+            diag = H[j + 1];
+            H[j + 1] = h;
+            if (h > colmax) colmax = h;
+            int hg = h - go; if (hg < 0) hg = 0;
+            e -= ge; if (e < 0) e = 0;
+            E[j + 1] = ORC_MAX(e, hg);
+            F -= ge; if (F < 0) F = 0;
+            F = ORC_MAX(F, hg);
+        }
+        if (colmax > max) {
+            max = colmax;
+            ec = i;
+            memcpy(saved, H, ((size_t) qL + 1) * sizeof(int));
+        }
+        if (terminate >= 0 && colmax == terminate) break;
+    }
+    int er = -1;
+    if (ec >= 0) {
+        for (int j = 0; j < qL; j++) if (saved[j + 1] == max) { er = j; break; }
+    }
+    *endCol = ec;
+    *endRow = er;
+    free(H); free(E); free(saved);
+    return max;
+}
+
+/* alignScoreEndPos<SEQ_SEQ>, StripedSmithWaterman.cpp:892-941: byte pass, word pass iff byte
+ * reports 255 (i.e. some column had max + bias >= 255, :238-242,:275).  out = score, qEnd, dbEnd, word */
+void orc_sw_score_endpos(const int16_t *mat, int A, const uint8_t *q, int qL, const int8_t *cb, int bias,
+                         const uint8_t *t, int tL, int go, int ge, int32_t *out) {
+    int ec, er;
+    int max = orc_gotoh(mat, A, q, cb, qL, 1, t, tL, 1, go, ge, -1, &ec, &er);
+    if (max + bias >= 255) {            /* word mode: exact up to INT16_MAX */
+        if (max > 32767) max = 32767;   /* adds_epi16 saturation; unreachable for BASELINE shapes */
+        out[0] = max; out[1] = (er < 0) ? qL - 1 : er; out[2] = (ec < 0) ? 0 : ec; out[3] = 1;
+    } else if (max == 0) {              /* byte mode, nothing aligned: end_db = -1; pvHmax is all zero so the
+                                           trace loop (:263-271) matches index 0 first */
+        out[0] = 0; out[1] = 0; out[2] = -1; out[3] = 0;
+    } else {
+        out[0] = max; out[1] = er; out[2] = ec; out[3] = 0;
+    }
+}
+
+/* ssw_align up to start positions (alignment modes 0/1; the E-value / coverage gate is applied by the
+ * caller: gate != 0 means "continue to start positions").  StripedSmithWaterman.cpp:831-890, :1129-1212.
+ * out = score, qStart, qEnd, dbStart, dbEnd, word */
+void orc_sw_align(const int16_t *mat, int A, const uint8_t *q, int qL, const int8_t *cb, int bias, const uint8_t *t,
+                  int tL, int go, int ge, int gate, int32_t *out) {
+    int32_t r[4];
+    orc_sw_score_endpos(mat, A, q, qL, cb, bias, t, tL, go, ge, r);
+    out[0] = r[0]; out[1] = -1; out[2] = r[1]; out[3] = -1; out[4] = r[2]; out[5] = r[3];
+    if (r[2] == -1 || !gate) return;
+    const int qEnd = r[1], dbEnd = r[2];
+    int ec, er;
+    int max = orc_gotoh(mat, A, q + qEnd, cb + qEnd, qEnd + 1, -1, t + dbEnd, dbEnd + 1, -1, go, ge, r[0], &ec, &er);
+    (void) max;
+    out[3] = dbEnd - ec;
+    out[1] = qEnd - er;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A1: per-diagonal scorer.  UngappedAlignment::createProfile :388-421 (profile[pos*21+a] =
+ * subMatrix[q[pos]][a] + cb4[pos], stored as char), scalarDiagonalScoring :45-57,
+ * computeSingelSequenceScores :423-437; count = min(255, score) (:283, T2).
+ * diagonal is the u16 as stored in CounterResult; lengths < 32768 only (T6).
+ * ------------------------------------------------------------------------------------------ */
+int orc_diag_score(const int16_t *mat, int A, const uint8_t *q, int qL, const int8_t *cb4, const uint8_t *t, int tL,
+                   uint16_t diagonal) {
+    int d = (int16_t) diagonal;
+    unsigned short dist1 = (unsigned short) (0 - diagonal), dist2 = diagonal;
+    int minDist = ORC_MIN(dist1, dist2);
+    int qOff, tOff, len;
+    if (d >= 0 && minDist < qL) {
+        qOff = minDist; tOff = 0; len = ORC_MIN(tL, qL - minDist);
+    } else if (d < 0 && minDist < tL) {
+        qOff = 0; tOff = minDist; len = ORC_MIN(tL - minDist, qL);
+    } else {
+        return 0;
+    }
+    int max = 0, score = 0;
+    for (int pos = 0; pos < len; pos++) {
+        int curr = (int8_t) (mat[(size_t) q[qOff + pos] * A + t[tOff + pos]] + cb4[qOff + pos]);
+        score += curr;
+        if (score < 0) score = 0;
+        if (score > max) max = score;
+    }
+    return max;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Batch drivers (OpenMP) -- one query against n targets laid out as SequenceLookup does
+ * (concatenated residues + offsets[n+1], SequenceLookup.cpp:42-46).
+ * ------------------------------------------------------------------------------------------ */
+void orc_ungapped_alignment_batch(const int16_t *mat, int A, const uint8_t *q, int qL, const int8_t *cb, int bias,
+                                  const uint8_t *tdata, const int64_t *toff, int64_t n, int32_t *out, int nthreads) {
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
+    for (int64_t i = 0; i < n; i++)
+        out[i] = orc_ungapped_alignment(mat, A, q, qL, cb, bias, tdata + toff[i], (int) (toff[i + 1] - toff[i]));
+}
+
+void orc_sw_score_endpos_batch(const int16_t *mat, int A, const uint8_t *q, int qL, const int8_t *cb, int bias,
+                               const uint8_t *tdata, const int64_t *toff, int64_t n, int go, int ge, int32_t *out,
+                               int nthreads) {
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
+    for (int64_t i = 0; i < n; i++)
+        orc_sw_score_endpos(mat, A, q, qL, cb, bias, tdata + toff[i], (int) (toff[i + 1] - toff[i]), go, ge, out + i * 4);
+}
+
+void orc_sw_align_batch(const int16_t *mat, int A, const uint8_t *q, int qL, const int8_t *cb, int bias,
+                        const uint8_t *tdata, const int64_t *toff, int64_t n, int go, int ge, const uint8_t *gate,
+                        int32_t *out, int nthreads) {
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads)
+    for (int64_t i = 0; i < n; i++)
+        orc_sw_align(mat, A, q, qL, cb, bias, tdata + toff[i], (int) (toff[i + 1] - toff[i]), go, ge,
+                     gate ? gate[i] : 1, out + i * 6);
+}
+
+void orc_diag_score_batch(const int16_t *mat, int A, const uint8_t *q, int qL, const int8_t *cb4, const uint8_t *tdata,
+                          const int64_t *toff, const uint32_t *hitIds, const uint16_t *hitDiags, int64_t nHits,
+                          uint8_t *counts, int32_t *raw) {
+    for (int64_t i = 0; i < nHits; i++) {
+        uint32_t id = hitIds[i];
+        int s = orc_diag_score(mat, A, q, qL, cb4, tdata + toff[id], (int) (toff[id + 1] - toff[id]), hitDiags[i]);
+        if (raw) raw[i] = s;
+        counts[i] = (uint8_t) ORC_MIN(255, s);
+    }
+}

@@ -1,0 +1,184 @@
+"""oracle/pyoracle.py -- TEST INFRASTRUCTURE: ctypes access to the CPU checker libraries.
+
+  Oracle()   -> oracle/liboracle.so          (C restatement, oracle/oracle.c)
+  Ref()      -> oracle/_ref/libmmseqs_ref.so (the reference's own sources compiled in place; optional)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "liboracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libmmseqs_ref.so")
+
+_vp = ctypes.c_void_p
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def build(with_ref=True):
+    """Compile the checker(s).  The reference library is only (re)built when /root/reference exists."""
+    subprocess.check_call(["make", "-s", "-C", HERE])
+    if with_ref and os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "ref"])
+
+
+def pack_targets(seqs):
+    """list of uint8 arrays -> (concatenated residues, int64 offsets[n+1]) as SequenceLookup lays them out."""
+    off = np.zeros(len(seqs) + 1, np.int64)
+    if len(seqs):
+        off[1:] = np.cumsum([len(s) for s in seqs])
+    data = np.concatenate(seqs).astype(np.uint8) if len(seqs) else np.zeros(0, np.uint8)
+    return np.ascontiguousarray(data), off
+
+
+class Oracle:
+    def __init__(self, mat, pback):
+        if not os.path.exists(ORACLE_SO):
+            build(with_ref=False)
+        self.lib = ctypes.CDLL(ORACLE_SO)
+        self.mat = np.ascontiguousarray(mat, np.int16)
+        self.pback = np.ascontiguousarray(pback, np.float64)
+        self.A = int(self.mat.shape[0])
+        self.lib.orc_ssw_bias.restype = ctypes.c_int
+        self.lib.orc_ungapped_alignment.restype = ctypes.c_int
+        self.lib.orc_diag_score.restype = ctypes.c_int
+
+    def comp_bias(self, q, scale=1.0):
+        q = np.ascontiguousarray(q, np.uint8)
+        out = np.zeros(len(q), np.float32)
+        self.lib.orc_comp_bias(_p(self.mat), _p(self.pback), self.A, _p(q), len(q), ctypes.c_float(scale), _p(out))
+        return out
+
+    def round_bias_ssw(self, f):
+        f = np.ascontiguousarray(f, np.float32)
+        out = np.zeros(len(f), np.int8)
+        self.lib.orc_round_bias_ssw(_p(f), len(f), _p(out))
+        return out
+
+    def round_bias_diag(self, f):
+        f = np.ascontiguousarray(f, np.float32)
+        out = np.zeros(len(f), np.int8)
+        self.lib.orc_round_bias_diag(_p(f), len(f), _p(out))
+        return out
+
+    def query_cb(self, q, comp_bias=True):
+        """int8 composition bias and profile bias constant exactly as ssw_init derives them."""
+        q = np.ascontiguousarray(q, np.uint8)
+        cb = self.round_bias_ssw(self.comp_bias(q)) if comp_bias else np.zeros(len(q), np.int8)
+        bias = self.lib.orc_ssw_bias(_p(self.mat), self.A, _p(cb), len(q), 1 if comp_bias else 0)
+        return cb, int(bias)
+
+    def ungapped(self, q, cb, bias, tdata, toff, nthreads=8):
+        q = np.ascontiguousarray(q, np.uint8)
+        n = len(toff) - 1
+        out = np.zeros(n, np.int32)
+        self.lib.orc_ungapped_alignment_batch(_p(self.mat), self.A, _p(q), len(q), _p(cb), bias, _p(tdata), _p(toff),
+                                              ctypes.c_int64(n), _p(out), nthreads)
+        return out
+
+    def sw_score_endpos(self, q, cb, bias, tdata, toff, go=11, ge=1, nthreads=8):
+        q = np.ascontiguousarray(q, np.uint8)
+        n = len(toff) - 1
+        out = np.zeros((n, 4), np.int32)
+        self.lib.orc_sw_score_endpos_batch(_p(self.mat), self.A, _p(q), len(q), _p(cb), bias, _p(tdata), _p(toff),
+                                           ctypes.c_int64(n), go, ge, _p(out), nthreads)
+        return out
+
+    def sw_align(self, q, cb, bias, tdata, toff, go=11, ge=1, gate=None, nthreads=8):
+        q = np.ascontiguousarray(q, np.uint8)
+        n = len(toff) - 1
+        out = np.zeros((n, 6), np.int32)
+        g = None if gate is None else np.ascontiguousarray(gate, np.uint8)
+        self.lib.orc_sw_align_batch(_p(self.mat), self.A, _p(q), len(q), _p(cb), bias, _p(tdata), _p(toff),
+                                    ctypes.c_int64(n), go, ge, _p(g), _p(out), nthreads)
+        return out
+
+    def diag(self, q, cb4, tdata, toff, hit_ids, hit_diags):
+        q = np.ascontiguousarray(q, np.uint8)
+        ids = np.ascontiguousarray(hit_ids, np.uint32)
+        dg = np.ascontiguousarray(hit_diags, np.uint16)
+        counts = np.zeros(len(ids), np.uint8)
+        raw = np.zeros(len(ids), np.int32)
+        self.lib.orc_diag_score_batch(_p(self.mat), self.A, _p(q), len(q), _p(cb4), _p(tdata), _p(toff), _p(ids),
+                                      _p(dg), ctypes.c_int64(len(ids)), _p(counts), _p(raw))
+        return counts, raw
+
+
+class Ref:
+    """The reference's own hot-path code (oracle/_ref).  available() is False on boxes without the build."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_SO)
+
+    def __init__(self):
+        self.lib = ctypes.CDLL(REF_SO)
+        self.lib.ref_init()
+        self.lib.ref_evalue.restype = ctypes.c_double
+
+    def matrix(self, nucl=False):
+        A = self.lib.ref_alphabet_size(1 if nucl else 0)
+        mat = np.zeros((A, A), np.int16)
+        pb = np.zeros(A, np.float64)
+        n2a = ctypes.create_string_buffer(A)
+        self.lib.ref_get_matrix(1 if nucl else 0, _p(mat), _p(pb), n2a)
+        return mat, pb, n2a.raw.decode()
+
+    def comp_bias(self, q, scale=1.0):
+        q = np.ascontiguousarray(q, np.uint8)
+        out = np.zeros(len(q), np.float32)
+        self.lib.ref_comp_bias(_p(q), len(q), ctypes.c_float(scale), _p(out))
+        return out
+
+    def ungapped(self, q, comp_bias, tdata, toff, nthreads=8):
+        q = np.ascontiguousarray(q, np.uint8)
+        n = len(toff) - 1
+        out = np.zeros(n, np.int32)
+        self.lib.ref_ungapped_alignment(_p(q), len(q), 1 if comp_bias else 0, _p(tdata), _p(toff), ctypes.c_int64(n),
+                                        _p(out), nthreads)
+        return out
+
+    def sw_score_endpos(self, q, comp_bias, tdata, toff, go=11, ge=1, nthreads=8):
+        q = np.ascontiguousarray(q, np.uint8)
+        n = len(toff) - 1
+        out = np.zeros((n, 4), np.int32)
+        self.lib.ref_sw_score_endpos(_p(q), len(q), 1 if comp_bias else 0, _p(tdata), _p(toff), ctypes.c_int64(n),
+                                     go, ge, _p(out), nthreads)
+        return out
+
+    def ssw_align(self, q, comp_bias, tdata, toff, go=11, ge=1, mode=1, eval_thr=1e300, cov_mode=0, cov_thr=0.0,
+                  db_residues=10**9, want_bt=False, nthreads=8):
+        q = np.ascontiguousarray(q, np.uint8)
+        n = len(toff) - 1
+        out = np.zeros((n, 10), np.int32)
+        ev = np.zeros(n, np.float64)
+        stride = 0
+        bt = None
+        if want_bt:
+            stride = int(len(q) + np.max(np.diff(toff)) + 8) if n else 8
+            bt = np.zeros(n * stride, np.uint8)
+        self.lib.ref_ssw_align(_p(q), len(q), 1 if comp_bias else 0, _p(tdata), _p(toff), ctypes.c_int64(n), go, ge,
+                               mode, ctypes.c_double(eval_thr), cov_mode, ctypes.c_float(cov_thr),
+                               ctypes.c_int64(db_residues), _p(out), _p(ev), _p(bt), ctypes.c_int64(stride), nthreads)
+        bts = None
+        if want_bt:
+            bts = [bytes(bt[i * stride:(i + 1) * stride]).split(b"\0", 1)[0].decode() for i in range(n)]
+        return out, ev, bts
+
+    def diag(self, q, bias_f32, tdata, toff, hit_ids, hit_diags):
+        q = np.ascontiguousarray(q, np.uint8)
+        ids = np.ascontiguousarray(hit_ids, np.uint32)
+        dg = np.ascontiguousarray(hit_diags, np.uint16)
+        counts = np.zeros(len(ids), np.uint8)
+        raw = np.zeros(len(ids), np.int32)
+        b = None if bias_f32 is None else np.ascontiguousarray(bias_f32, np.float32)
+        self.lib.ref_diag_align(_p(q), len(q), _p(b), _p(tdata), _p(toff), ctypes.c_int64(len(toff) - 1), _p(ids),
+                                _p(dg), ctypes.c_int64(len(ids)), _p(counts), _p(raw))
+        return counts, raw
