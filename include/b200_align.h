@@ -1,0 +1,117 @@
+/* include/b200_align.h -- C ABI of libb200align.so: MMseqs2's alignment hot path on one B200 (sm_100a).
+ *
+ * Plain C, opaque handles, int status codes, caller-allocated outputs, no exceptions (the MMseqs2 host is
+ * built -fno-exceptions, src/CMakeLists.txt:97-100).  One b200_ctx owns one GPU, one stream and the
+ * resident target DB; calls on one ctx are serialised by an internal mutex, so the per-OpenMP-thread
+ * operator objects of the reference (QueryMatcher.cpp:73, Alignment.cpp:295) can share it.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the MMseqs2 tree):
+ *
+ *   b200_db_load            Marv::loadDb/setDb (lib/libmarv/src/marv.h:20-24) and SequenceLookup
+ *                           (src/prefiltering/SequenceLookup.cpp:42-46): concatenated numeric residues + offsets.
+ *   b200_ungapped_scan      SmithWaterman::ungapped_alignment (src/alignment/StripedSmithWaterman.cpp:1817-1876)
+ *                           over every target + the filter/sort/truncate of runFilterOnCpu
+ *                           (src/prefiltering/ungappedprefilter.cpp:418-478); same role as Marv::scan (marv.h:47).
+ *   b200_diag_score         UngappedAlignment::align / scoreSingelSequenceByCounterResult
+ *                           (src/prefiltering/UngappedAlignment.cpp:36-42, 440-460).
+ *   b200_sw_score_endpos    SmithWaterman::alignScoreEndPos (StripedSmithWaterman.cpp:892-941).
+ *   b200_sw_startpos        the reverse pass of SmithWaterman::alignStartPosBacktrace (:1129-1212).
+ *   b200_sw_align           ssw_align alignment modes 0/1 (:831-890) with the E-value/coverage gate supplied
+ *                           by the caller (host double math stays in the reference: EvalueComputation.h:18-40).
+ *
+ * Query profiles are int8, layout [A][qlen] (profile[a*qlen + j] = score of query position j against residue a,
+ * composition bias already folded in, NO bias offset added) -- the layout Marv::scan takes
+ * (ungappedprefilter.cpp:195-203) and SmithWaterman::profile_word_linear holds (StripedSmithWaterman.cpp:1434-1439).
+ */
+#ifndef B200_ALIGN_H
+#define B200_ALIGN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_ctx b200_ctx;
+typedef struct b200_job b200_job;
+
+enum {
+    B200_OK = 0,
+    B200_ERR_CUDA = -1,   /* a CUDA runtime call failed; see b200_last_error */
+    B200_ERR_ARG = -2,    /* bad argument (NULL, negative length, id out of range, ...) */
+    B200_ERR_NODB = -3,   /* no target DB loaded */
+    B200_ERR_RANGE = -4,  /* input outside the supported domain (e.g. sequence >= 32768 for the diagonal scorer, T6) */
+    B200_ERR_NOMEM = -5
+};
+
+typedef struct {
+    const int8_t *profile; /* [A][qlen], host memory */
+    int32_t qlen;
+    int32_t bias;          /* SSW profile bias = |min(mat)| + |min(0, min cb)| (StripedSmithWaterman.cpp:1397-1406);
+                              drives the u8 saturation of the scan (T1) and the byte->word rule (T5) */
+} b200_query;
+
+typedef struct { uint32_t id; int32_t score; } b200_hit;                 /* ordered: score desc, id asc */
+typedef struct { uint32_t query; uint32_t target; } b200_pair;           /* query = index into queries[], target = DB id */
+typedef struct { int32_t score, qend, dbend, word; } b200_sw_end;        /* s_align score1,qEndPos1,dbEndPos1,word */
+typedef struct { int32_t score, qstart, qend, dbstart, dbend, word; } b200_sw_aln;
+
+/* ---- context -------------------------------------------------------------------------------- */
+int b200_create(int device, b200_ctx **ctx);
+void b200_destroy(b200_ctx *ctx);
+const char *b200_last_error(const b200_ctx *ctx);
+int b200_device_info(const b200_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, uint64_t *hbm_bytes);
+/* kernels launched by this ctx since creation (bench.py reports the delta as gpu_launches) */
+uint64_t b200_launch_count(const b200_ctx *ctx);
+/* CUDA events on the ctx stream, for device-side timing of resident-input runs */
+int b200_event_record(b200_ctx *ctx, int slot /*0..15*/);
+int b200_event_elapsed_ms(b200_ctx *ctx, int slot_a, int slot_b, float *ms); /* synchronises on slot_b */
+int b200_sync(b200_ctx *ctx);
+
+/* ---- target DB ------------------------------------------------------------------------------- */
+/* residues: numeric codes 0..alphabet-1, sequence i = residues[offsets[i] .. offsets[i+1]).  Copied to HBM. */
+int b200_db_load(b200_ctx *ctx, const uint8_t *residues, const uint64_t *offsets, uint64_t n_seq, int alphabet);
+uint64_t b200_db_num_seqs(const b200_ctx *ctx);
+uint64_t b200_db_num_residues(const b200_ctx *ctx);
+
+/* ---- A2: all-diagonals ungapped scan ---------------------------------------------------------- */
+/* For each query: score every DB sequence; keep score > min_score_excl; order by (score desc, id asc);
+ * truncate to max_hits.  hits: [n_queries][max_hits]; n_hits: [n_queries].
+ * dense (optional, may be NULL): [n_queries][n_seq] raw scores as u8 (0..255). */
+int b200_ungapped_scan(b200_ctx *ctx, const b200_query *queries, int n_queries, int min_score_excl,
+                       uint32_t max_hits, b200_hit *hits, uint32_t *n_hits, uint8_t *dense);
+
+/* ---- A1: per-diagonal scorer ------------------------------------------------------------------ */
+/* One query; hit i = (ids[i], diagonals[i]).  counts in/out: entries that are non-zero on input are skipped
+ * (UngappedAlignment.cpp:327-329); others receive min(255, score).  raw (optional): unclamped score for
+ * every hit (scoreSingleSequence).  The profile here is the diagonal scorer's own (bias/4 rounding,
+ * UngappedAlignment.cpp:395-400); q->bias is ignored. */
+int b200_diag_score(b200_ctx *ctx, const b200_query *q, const uint32_t *ids, const uint16_t *diagonals, uint64_t n,
+                    uint8_t *counts, int32_t *raw);
+
+/* ---- A3-A5: affine-gap local alignment --------------------------------------------------------- */
+int b200_sw_score_endpos(b200_ctx *ctx, const b200_query *queries, int n_queries, const b200_pair *pairs, uint64_t n,
+                         int gap_open, int gap_extend, b200_sw_end *out);
+/* ends[i] is the result of b200_sw_score_endpos for pairs[i]; pairs with ends[i].dbend == -1 are passed through */
+int b200_sw_startpos(b200_ctx *ctx, const b200_query *queries, int n_queries, const b200_pair *pairs, uint64_t n,
+                     int gap_open, int gap_extend, const b200_sw_end *ends, b200_sw_aln *out);
+/* score + end for every pair, start positions for pairs with gate[i] != 0 (gate == NULL: all) */
+int b200_sw_align(b200_ctx *ctx, const b200_query *queries, int n_queries, const b200_pair *pairs, uint64_t n,
+                  int gap_open, int gap_extend, const uint8_t *gate, b200_sw_aln *out);
+
+/* ---- resident-input jobs (inputs staged in HBM once, run many times; used for kernel-only timing) ----- */
+int b200_scan_job_create(b200_ctx *ctx, const b200_query *queries, int n_queries, int min_score_excl,
+                         uint32_t max_hits, b200_job **job);
+int b200_sw_job_create(b200_ctx *ctx, const b200_query *queries, int n_queries, const b200_pair *pairs, uint64_t n,
+                       int gap_open, int gap_extend, b200_job **job);
+int b200_job_run(b200_job *job);                       /* enqueue on the ctx stream; does not synchronise */
+int b200_scan_job_fetch(b200_job *job, b200_hit *hits, uint32_t *n_hits, uint8_t *dense);
+int b200_sw_job_fetch(b200_job *job, b200_sw_end *out);
+uint64_t b200_job_cells(const b200_job *job);          /* sum over work items of qlen*tlen (GCUPS numerator) */
+void b200_job_destroy(b200_job *job);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_ALIGN_H */

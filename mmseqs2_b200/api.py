@@ -1,0 +1,288 @@
+"""ctypes binding of libb200align.so, shaped after the reference operator surface.
+
+Reference interface            ->  here
+  SubstitutionMatrix / BaseMatrix (subMatrix, pBack)                 SubMatrix
+  SmithWaterman::ssw_init (StripedSmithWaterman.cpp:1364)            SubMatrix.ssw_query()      -> QueryProfile
+  UngappedAlignment::createProfile (UngappedAlignment.cpp:388)       SubMatrix.diag_query()     -> QueryProfile
+  Marv::loadDb/setDb (marv.h:20-24), SequenceLookup                  Context.load_db()
+  Marv::scan / SmithWaterman::ungapped_alignment over the DB         Context.ungapped_scan()
+  UngappedAlignment::align / scoreSingleSequence                     Context.diag_score()
+  SmithWaterman::alignScoreEndPos                                    Context.sw_score_endpos()
+  SmithWaterman::ssw_align (modes 0/1)                               Context.sw_align()
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_vp = ctypes.c_void_p
+_u64 = ctypes.c_uint64
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libb200align.so")
+
+
+def load_library():
+    """Load libb200align.so; fail loudly if it was not built (no fallback of any kind)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise B200Error("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(the CUDA library is the product; there is no CPU path)" % p)
+    lib = ctypes.CDLL(p)
+    lib.b200_last_error.restype = ctypes.c_char_p
+    lib.b200_last_error.argtypes = [_vp]
+    for name in ("b200_launch_count", "b200_db_num_seqs", "b200_db_num_residues", "b200_job_cells"):
+        getattr(lib, name).restype = _u64
+        getattr(lib, name).argtypes = [_vp]
+    lib.b200_destroy.argtypes = [_vp]
+    lib.b200_destroy.restype = None
+    lib.b200_job_destroy.argtypes = [_vp]
+    lib.b200_job_destroy.restype = None
+    _LIB = lib
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+class _CQuery(ctypes.Structure):
+    _fields_ = [("profile", _vp), ("qlen", ctypes.c_int32), ("bias", ctypes.c_int32)]
+
+
+HIT_DTYPE = np.dtype([("id", np.uint32), ("score", np.int32)])
+PAIR_DTYPE = np.dtype([("query", np.uint32), ("target", np.uint32)])
+END_DTYPE = np.dtype([("score", np.int32), ("qend", np.int32), ("dbend", np.int32), ("word", np.int32)])
+ALN_DTYPE = np.dtype([("score", np.int32), ("qstart", np.int32), ("qend", np.int32), ("dbstart", np.int32),
+                      ("dbend", np.int32), ("word", np.int32)])
+
+
+class QueryProfile:
+    """int8 [A][qlen] profile + the SSW bias constant (what ssw_init leaves in s_profile)."""
+
+    def __init__(self, profile, bias=0, cb=None):
+        self.profile = np.ascontiguousarray(profile, np.int8)
+        self.A, self.qlen = self.profile.shape
+        self.bias = int(bias)
+        self.cb = cb
+
+
+class SubMatrix:
+    """Integer substitution matrix + background; builds query profiles with the reference's rounding rules (host)."""
+
+    def __init__(self, mat, pback):
+        self.lib = load_library()
+        self.mat = np.ascontiguousarray(mat, np.int16)
+        self.pback = np.ascontiguousarray(pback, np.float64)
+        self.A = int(self.mat.shape[0])
+        self.lib.b200h_ssw_bias.restype = ctypes.c_int
+        self.lib.b200h_build_profile.restype = ctypes.c_int
+
+    def comp_bias(self, q, scale=1.0):
+        q = np.ascontiguousarray(q, np.uint8)
+        out = np.zeros(len(q), np.float32)
+        self.lib.b200h_comp_bias(_p(self.mat), _p(self.pback), self.A, _p(q), len(q), ctypes.c_float(scale), _p(out))
+        return out
+
+    def ssw_query(self, q, comp_bias=True, scale=1.0):
+        """SmithWaterman::ssw_init for a sequence query: profile[a][j] = mat[a][q[j]] + cb[j], bias constant."""
+        q = np.ascontiguousarray(q, np.uint8)
+        cb = np.zeros(len(q), np.int8)
+        if comp_bias:
+            f = self.comp_bias(q, scale)
+            self.lib.b200h_round_bias_ssw(_p(f), len(q), _p(cb))
+        bias = self.lib.b200h_ssw_bias(_p(self.mat), self.A, _p(cb), len(q), 1 if comp_bias else 0)
+        prof = np.zeros((self.A, len(q)), np.int8)
+        if self.lib.b200h_build_profile(_p(self.mat), self.A, _p(q), len(q), _p(cb), 1, _p(prof)) != 0:
+            raise B200Error("profile value outside int8")
+        return QueryProfile(prof, bias, cb)
+
+    def diag_query(self, q, bias_f32=None):
+        """UngappedAlignment::createProfile: profile[a][j] = mat[q[j]][a] + round(bias[j]/4)."""
+        q = np.ascontiguousarray(q, np.uint8)
+        cb = np.zeros(len(q), np.int8)
+        if bias_f32 is not None:
+            f = np.ascontiguousarray(bias_f32, np.float32)
+            self.lib.b200h_round_bias_diag(_p(f), len(q), _p(cb))
+        prof = np.zeros((self.A, len(q)), np.int8)
+        if self.lib.b200h_build_profile(_p(self.mat), self.A, _p(q), len(q), _p(cb), 0, _p(prof)) != 0:
+            raise B200Error("profile value outside int8")
+        return QueryProfile(prof, 0, cb)
+
+
+def _cqueries(queries):
+    arr = (_CQuery * len(queries))()
+    for i, q in enumerate(queries):
+        arr[i].profile = q.profile.ctypes.data
+        arr[i].qlen = q.qlen
+        arr[i].bias = q.bias
+    return arr
+
+
+class Job:
+    def __init__(self, ctx, handle, kind, nq=0, k=0, n=0):
+        self.ctx, self.handle, self.kind, self.nq, self.k, self.n = ctx, handle, kind, nq, k, n
+
+    def run(self):
+        self.ctx._check(self.ctx.lib.b200_job_run(self.handle))
+
+    @property
+    def cells(self):
+        return int(self.ctx.lib.b200_job_cells(self.handle))
+
+    def fetch(self, want_dense=False):
+        ctx = self.ctx
+        if self.kind == "scan":
+            hits = np.zeros((self.nq, self.k), HIT_DTYPE)
+            n_hits = np.zeros(self.nq, np.uint32)
+            dense = np.zeros((self.nq, ctx.n_seq), np.uint8) if want_dense else None
+            ctx._check(ctx.lib.b200_scan_job_fetch(self.handle, _p(hits), _p(n_hits), _p(dense)))
+            return hits, n_hits, dense
+        out = np.zeros(self.n, END_DTYPE)
+        ctx._check(ctx.lib.b200_sw_job_fetch(self.handle, _p(out)))
+        return out
+
+    def close(self):
+        if self.handle:
+            self.ctx.lib.b200_job_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """One GPU, one stream, one resident target DB (the role of class Marv / SequenceLookup)."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = _vp()
+        rc = self.lib.b200_create(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise B200Error("b200_create(%d) failed with %d (is a CUDA device visible?)" % (device, rc))
+        self.h = h
+        self.n_seq = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B200Error("b200 error %d: %s" % (rc, self.lib.b200_last_error(self.h).decode()))
+
+    def device_info(self):
+        sm, ma, mi, hbm = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), _u64()
+        self._check(self.lib.b200_device_info(self.h, ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi), ctypes.byref(hbm)))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "hbm_bytes": hbm.value}
+
+    @property
+    def launches(self):
+        return int(self.lib.b200_launch_count(self.h))
+
+    def sync(self):
+        self._check(self.lib.b200_sync(self.h))
+
+    def event_record(self, slot):
+        self._check(self.lib.b200_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = ctypes.c_float()
+        self._check(self.lib.b200_event_elapsed_ms(self.h, a, b, ctypes.byref(ms)))
+        return ms.value
+
+    # ---- DB
+    def load_db(self, residues, offsets, alphabet):
+        residues = np.ascontiguousarray(residues, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        self._check(self.lib.b200_db_load(self.h, _p(residues), _p(offsets), _u64(len(offsets) - 1), int(alphabet)))
+        self.n_seq = len(offsets) - 1
+
+    # ---- A2
+    def ungapped_scan(self, queries, min_score_excl=15, max_hits=300, want_dense=False):
+        cq = _cqueries(queries)
+        nq = len(queries)
+        hits = np.zeros((nq, max_hits), HIT_DTYPE)
+        n_hits = np.zeros(nq, np.uint32)
+        dense = np.zeros((nq, self.n_seq), np.uint8) if want_dense else None
+        self._check(self.lib.b200_ungapped_scan(self.h, cq, nq, int(min_score_excl), ctypes.c_uint32(max_hits), _p(hits),
+                                                _p(n_hits), _p(dense)))
+        return hits, n_hits, dense
+
+    def scan_job(self, queries, min_score_excl=15, max_hits=300):
+        cq = _cqueries(queries)
+        h = _vp()
+        self._check(self.lib.b200_scan_job_create(self.h, cq, len(queries), int(min_score_excl), ctypes.c_uint32(max_hits),
+                                                  ctypes.byref(h)))
+        return Job(self, h, "scan", nq=len(queries), k=max_hits)
+
+    # ---- A1
+    def diag_score(self, query, ids, diagonals, counts=None, want_raw=False):
+        ids = np.ascontiguousarray(ids, np.uint32)
+        dg = np.ascontiguousarray(diagonals, np.uint16)
+        cnt = np.zeros(len(ids), np.uint8) if counts is None else np.ascontiguousarray(counts, np.uint8).copy()
+        raw = np.zeros(len(ids), np.int32) if want_raw else None
+        cq = _cqueries([query])
+        self._check(self.lib.b200_diag_score(self.h, cq, _p(ids), _p(dg), _u64(len(ids)), _p(cnt), _p(raw)))
+        return cnt, raw
+
+    # ---- A3-A5
+    @staticmethod
+    def _pairs(pairs):
+        arr = np.zeros(len(pairs), PAIR_DTYPE)
+        pairs = np.asarray(pairs)
+        if len(pairs):
+            arr["query"] = pairs[:, 0]
+            arr["target"] = pairs[:, 1]
+        return arr
+
+    def sw_score_endpos(self, queries, pairs, go=11, ge=1):
+        cq = _cqueries(queries)
+        pa = pairs if getattr(pairs, "dtype", None) == PAIR_DTYPE else self._pairs(pairs)
+        out = np.zeros(len(pa), END_DTYPE)
+        self._check(self.lib.b200_sw_score_endpos(self.h, cq, len(queries), _p(pa), _u64(len(pa)), go, ge, _p(out)))
+        return out
+
+    def sw_startpos(self, queries, pairs, ends, go=11, ge=1):
+        cq = _cqueries(queries)
+        pa = pairs if getattr(pairs, "dtype", None) == PAIR_DTYPE else self._pairs(pairs)
+        ends = np.ascontiguousarray(ends, END_DTYPE)
+        out = np.zeros(len(pa), ALN_DTYPE)
+        self._check(self.lib.b200_sw_startpos(self.h, cq, len(queries), _p(pa), _u64(len(pa)), go, ge, _p(ends), _p(out)))
+        return out
+
+    def sw_align(self, queries, pairs, go=11, ge=1, gate=None):
+        cq = _cqueries(queries)
+        pa = pairs if getattr(pairs, "dtype", None) == PAIR_DTYPE else self._pairs(pairs)
+        g = None if gate is None else np.ascontiguousarray(gate, np.uint8)
+        out = np.zeros(len(pa), ALN_DTYPE)
+        self._check(self.lib.b200_sw_align(self.h, cq, len(queries), _p(pa), _u64(len(pa)), go, ge, _p(g), _p(out)))
+        return out
+
+    def sw_job(self, queries, pairs, go=11, ge=1):
+        cq = _cqueries(queries)
+        pa = pairs if getattr(pairs, "dtype", None) == PAIR_DTYPE else self._pairs(pairs)
+        h = _vp()
+        self._check(self.lib.b200_sw_job_create(self.h, cq, len(queries), _p(pa), _u64(len(pa)), go, ge, ctypes.byref(h)))
+        return Job(self, h, "sw", n=len(pa))

@@ -1,0 +1,1310 @@
+// mmseqs2_b200/csrc/b200_align.cu -- libb200align.so: MMseqs2's alignment hot path, hand-written for sm_100a.
+//
+// Kernels (see DESIGN.md for layouts and rooflines):
+//   ungapped_scan_kernel<G,K>  A2  all-diagonals ungapped scan, int16x2 DPX (__viaddmin_s16x2_relu), profile in smem
+//   topk_select_kernel         A2  per-query histogram cut-off + ordered compaction of the u8 score vector
+//   diag_score_kernel          A1  per-(target,diagonal) max-prefix score as a parallel max-subarray reduction
+//   pad_profile_kernel             [A][qlen] int8 -> padded forward / reversed device profiles
+//   sw32_kernel<DIR>           A3-A5 affine-gap local DP, one warp per pair, int32 DPX (__viaddmax_s32), wavefront over
+//                              lanes, score + end position in one pass; DIR=-1 is the reverse (start position) pass
+//
+// Semantics follow the reference (cited per function); nothing here is derived from lib/libmarv.
+#include "b200_align.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+#define CU_TRY(ctx, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                     \
+            return B200_ERR_CUDA;                                                                 \
+        }                                                                                         \
+    } while (0)
+
+static inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
+
+struct DevBuf {  // grow-only device scratch
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct QueryDesc {     // device-side description of one query profile
+    uint64_t raw_off;  // byte offset of the raw [A][qlen] int8 profile in d_raw
+    uint64_t pad_off;  // byte offset of the padded [(A+1)][Lp] profile in d_pad (forward; reversed copy follows at +rev_off)
+    uint64_t rev_off;
+    int32_t qlen;
+    int32_t Lp;
+    int32_t bias;
+    int32_t pad_;
+};
+
+struct PairDesc {  // one (query,target) work unit of the gapped kernel, device side
+    uint32_t target;
+    int32_t qend;   // reverse pass only
+    int32_t dbend;  // reverse pass only
+    int32_t score;  // reverse pass only: terminate value
+};
+
+struct WorkItem {  // one CTA's share: pairs [p0,p1) of one query
+    uint32_t query;
+    uint32_t p0;
+    uint32_t p1;
+    uint32_t pad_;
+};
+
+struct b200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[16];
+    std::mutex mu;
+    std::string err;
+    uint64_t launches = 0;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    uint64_t hbm = 0;
+    int max_smem_optin = 0;
+    // resident target DB
+    uint8_t *d_res = nullptr;     // residues, every sequence 16-byte aligned and padded with code `alphabet`
+    uint64_t *d_off = nullptr;    // [n_seq] byte offset of sequence i in d_res
+    int32_t *d_len = nullptr;     // [n_seq]
+    uint32_t *d_order = nullptr;  // [n_seq] ids sorted by length descending (scan schedule)
+    std::vector<int32_t> h_len;
+    uint64_t n_seq = 0, n_res = 0;
+    int alphabet = 0;
+    int max_len = 0;
+    // scratch
+    DevBuf raw, pad, qdesc, dense, hits, nhits, pairs, items, out4, bnd, ids, diags, counts, rawout, counter;
+};
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack16(int lo, int hi) {
+    return (uint32_t) (lo & 0xffff) | ((uint32_t) (hi & 0xffff) << 16);
+}
+
+// 1-D bulk (TMA) copy global -> shared, completion on an mbarrier.  bytes % 16 == 0, both pointers 16-byte aligned.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    unsigned a = (unsigned) __cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    unsigned a = (unsigned) __cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar) {
+    unsigned d = (unsigned) __cvta_generic_to_shared(smem_dst);
+    unsigned b = (unsigned) __cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+                 "l"(gsrc), "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    unsigned a = (unsigned) __cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// A2: all-diagonals ungapped scan.
+// Reference semantics: SmithWaterman::ungapped_alignment, StripedSmithWaterman.cpp:1817-1876 --
+//   S(j,i) = subs_u8(adds_u8(S(j-1,i-1), s(j,i)+bias), bias)  ==  max(0, min(S(j-1,i-1) + s(j,i), 255-bias))
+// i.e. exactly one __viaddmin_s16x2_relu per two cells.
+//
+// A group of G lanes owns one target; a lane keeps K packed registers = 2K query rows.  Only the (i-1,j-1)
+// dependency exists, so all lanes sit on the SAME target column (no wavefront skew).  To avoid a per-register
+// shift for the diagonal move, columns alternate between two row packings:
+//   V-form  reg r = rows (b+2r,   b+2r+1)     W-form  reg r = rows (b+2r-1, b+2r)        (b = first row of the lane)
+//   V(i+1)[r] = f(W(i)[r]   + P [a][r])        same register, no data movement
+//   W(i+2)[r] = f(V(i+1)[r-1] + P'[a][r])      shift by one whole register (descending in-place), one shuffle per lane
+// P / P' are the two packings of the int16 query profile, staged in shared memory, laid out [a][c][g] as uint4 so
+// that a group's LDS.128 is conflict-free.
+// ------------------------------------------------------------------------------------------------
+template <int G, int K>
+__global__ void __launch_bounds__(256)
+ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict__ qd, const uint8_t *__restrict__ db,
+                     const uint64_t *__restrict__ off, const int32_t *__restrict__ len,
+                     const uint32_t *__restrict__ order, uint32_t n_seq, int A, uint8_t *__restrict__ out) {
+    static_assert(K % 4 == 0, "K must be a multiple of 4");
+    constexpr int C = K / 4;
+    constexpr int ROW_U4 = C * G;  // uint4 per residue row
+    extern __shared__ uint4 smem_u4[];
+    uint4 *P = smem_u4;
+    uint4 *Pp = smem_u4 + (size_t) (A + 1) * ROW_U4;
+
+    const QueryDesc q = qd[blockIdx.y];
+    const int8_t *prof = raw + q.raw_off;
+    const int qlen = q.qlen;
+    {
+        uint32_t *Pw = reinterpret_cast<uint32_t *>(P);
+        uint32_t *Ppw = reinterpret_cast<uint32_t *>(Pp);
+        const int words = G * K;
+        for (int idx = threadIdx.x; idx < (A + 1) * words; idx += blockDim.x) {
+            const int a = idx / words, w = idx % words;
+            const int g = w / K, r = w % K, c = r >> 2, e = r & 3;
+            int s0 = 0, s1 = 0, sm1 = 0;  // rows 2w, 2w+1, 2w-1
+            if (a < A) {
+                const int8_t *pa = prof + (size_t) a * qlen;
+                if (2 * w < qlen) s0 = pa[2 * w];
+                if (2 * w + 1 < qlen) s1 = pa[2 * w + 1];
+                if (2 * w - 1 >= 0 && 2 * w - 1 < qlen) sm1 = pa[2 * w - 1];
+            }
+            const int dst = (a * ROW_U4 + c * G + g) * 4 + e;
+            Pw[dst] = pack16(s0, s1);
+            Ppw[dst] = pack16(sm1, s0);
+        }
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int g = lane % G;
+    constexpr int GROUPS_PER_WARP = 32 / G;
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    const uint32_t warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t cst = (uint32_t) (255 - q.bias) * 0x00010001u;
+    const uint32_t padword = (uint32_t) A * 0x01010101u;
+    uint8_t *outq = out + (size_t) blockIdx.y * n_seq;
+
+    for (uint32_t base = warp_id * GROUPS_PER_WARP; base < n_seq; base += warps_total * GROUPS_PER_WARP) {
+        const uint32_t it = base + lane / G;
+        uint32_t tid = 0;
+        int tl = 0;
+        if (it < n_seq) { tid = order[it]; tl = len[tid]; }
+        const uint4 *tp = reinterpret_cast<const uint4 *>(db + off[tid]);
+        int maxl = tl;
+#pragma unroll
+        for (int o = 16; o >= G; o >>= 1) maxl = max(maxl, __shfl_xor_sync(0xffffffffu, maxl, o));
+
+        uint32_t S[K];
+#pragma unroll
+        for (int r = 0; r < K; r++) S[r] = 0;
+        uint32_t best = 0;
+
+        for (int i0 = 0; i0 < maxl; i0 += 16) {
+            uint4 ch = make_uint4(padword, padword, padword, padword);
+            if (i0 < tl) ch = __ldg(tp + (i0 >> 4));
+            const uint32_t cw[4] = {ch.x, ch.y, ch.z, ch.w};
+#pragma unroll
+            for (int u = 0; u < 16; u += 2) {
+                const uint32_t wv = cw[u >> 2];
+                const uint32_t a0 = (wv >> (8 * (u & 3))) & 0xffu;
+                const uint32_t a1 = (wv >> (8 * ((u + 1) & 3))) & 0xffu;
+                {   // even column: V from W, same registers
+                    const uint4 *p = P + a0 * ROW_U4 + g;
+#pragma unroll
+                    for (int c = 0; c < C; c++) {
+                        const uint4 x = p[c * G];
+                        S[4 * c + 0] = __viaddmin_s16x2_relu(S[4 * c + 0], x.x, cst);
+                        S[4 * c + 1] = __viaddmin_s16x2_relu(S[4 * c + 1], x.y, cst);
+                        S[4 * c + 2] = __viaddmin_s16x2_relu(S[4 * c + 2], x.z, cst);
+                        S[4 * c + 3] = __viaddmin_s16x2_relu(S[4 * c + 3], x.w, cst);
+                    }
+#pragma unroll
+                    for (int r = 0; r < K; r += 2) best = __vimax3_s16x2(best, S[r], S[r + 1]);
+                }
+                {   // odd column: W from V, shifted by one register
+                    uint32_t carry = __shfl_up_sync(0xffffffffu, S[K - 1], 1, G);
+                    if (g == 0) carry = 0;
+                    const uint4 *p = Pp + a1 * ROW_U4 + g;
+                    uint4 x[C];
+#pragma unroll
+                    for (int c = 0; c < C; c++) x[c] = p[c * G];
+#pragma unroll
+                    for (int c = C - 1; c >= 0; c--) {
+                        S[4 * c + 3] = __viaddmin_s16x2_relu(S[4 * c + 2], x[c].w, cst);
+                        S[4 * c + 2] = __viaddmin_s16x2_relu(S[4 * c + 1], x[c].z, cst);
+                        S[4 * c + 1] = __viaddmin_s16x2_relu(S[4 * c + 0], x[c].y, cst);
+                        S[4 * c + 0] = __viaddmin_s16x2_relu(c > 0 ? S[4 * c - 1] : carry, x[c].x, cst);
+                    }
+#pragma unroll
+                    for (int r = 0; r < K; r += 2) best = __vimax3_s16x2(best, S[r], S[r + 1]);
+                }
+            }
+        }
+        int m = max((int) (best & 0xffffu), (int) (best >> 16));
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (g == 0 && it < n_seq) outq[tid] = (uint8_t) m;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// A2 epilogue: per query keep score > thr, order (score desc, id asc), truncate to k.
+// (runFilterOnCpu: ungappedprefilter.cpp:450-478; comparator compareHitsByScoreAndId.)
+// One CTA per query: 256-bin histogram -> cut-off score -> ordered (by id) compaction.  The final sort of the
+// <= k survivors happens on the host.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+topk_select_kernel(const uint8_t *__restrict__ dense, uint32_t n_seq, int thr, uint32_t k, b200_hit *__restrict__ hits,
+                   uint32_t *__restrict__ n_hits) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t warp_sums[32][2];
+    __shared__ int s_cut;
+    __shared__ uint32_t s_need, s_total, s_base_hi, s_base_tie;
+    const uint8_t *sc = dense + (size_t) blockIdx.x * n_seq;
+    b200_hit *oh = hits + (size_t) blockIdx.x * k;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_seq; i += blockDim.x) atomicAdd(&hist[sc[i]], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t cum = 0;
+        int cut = thr;  // keep everything > cut, plus `need` smallest-id entries == cut
+        uint32_t need = 0;
+        for (int s = 255; s > thr; s--) {
+            if (cum + hist[s] > k) { cut = s; need = k - cum; break; }
+            cum += hist[s];
+        }
+        s_cut = cut; s_need = need; s_total = cum + need; s_base_hi = 0; s_base_tie = 0;
+    }
+    __syncthreads();
+    const int cut = s_cut;
+    const uint32_t need = s_need;
+    const bool take_ties = need > 0;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t i0 = 0; i0 < n_seq; i0 += blockDim.x) {
+        const uint32_t i = i0 + threadIdx.x;
+        int s = (i < n_seq) ? (int) sc[i] : -0x7fffffff;
+        const bool hi = s > cut;
+        const bool tie = take_ties && s == cut;
+        const unsigned bh = __ballot_sync(0xffffffffu, hi), bt = __ballot_sync(0xffffffffu, tie);
+        if (lane == 0) { warp_sums[wid][0] = __popc(bh); warp_sums[wid][1] = __popc(bt); }
+        __syncthreads();
+        uint32_t pre_h = 0, pre_t = 0;
+        for (int w = 0; w < wid; w++) { pre_h += warp_sums[w][0]; pre_t += warp_sums[w][1]; }
+        const uint32_t lm = (1u << lane) - 1u;
+        const uint32_t rh = s_base_hi + pre_h + __popc(bh & lm);
+        const uint32_t rt = s_base_tie + pre_t + __popc(bt & lm);
+        const uint32_t n_hi_total = s_total - need;  // entries strictly above the cut
+        if (hi) { oh[rh].id = i; oh[rh].score = s; }
+        if (tie && rt < need) { oh[n_hi_total + rt].id = i; oh[n_hi_total + rt].score = s; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t th = 0, tt = 0;
+            for (int w = 0; w < (int) (blockDim.x >> 5); w++) { th += warp_sums[w][0]; tt += warp_sums[w][1]; }
+            s_base_hi += th; s_base_tie += tt;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) n_hits[blockIdx.x] = s_total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// A1: per-diagonal scorer.  UngappedAlignment.cpp:45-57 (scalarDiagonalScoring), :423-437 (segment selection),
+// :283 (min(255,.)).  max over prefixes of the 0-reset running sum == maximum-subarray sum, which is associative:
+// each lane scans a contiguous chunk into (sum, best prefix, best suffix, best), then an ordered tree combine.
+// ------------------------------------------------------------------------------------------------
+struct Seg { int sum, pre, suf, best; };
+__device__ __forceinline__ Seg seg_combine(const Seg &L, const Seg &R) {
+    Seg o;
+    o.sum = L.sum + R.sum;
+    o.pre = max(L.pre, L.sum + R.pre);
+    o.suf = max(R.suf, R.sum + L.suf);
+    o.best = max(max(L.best, R.best), L.suf + R.pre);
+    return o;
+}
+
+__global__ void __launch_bounds__(256)
+diag_score_kernel(const int8_t *__restrict__ prof, int qlen, const uint8_t *__restrict__ db,
+                  const uint64_t *__restrict__ off, const int32_t *__restrict__ len, const uint32_t *__restrict__ ids,
+                  const uint16_t *__restrict__ diags, uint64_t n, uint8_t *__restrict__ counts,
+                  int32_t *__restrict__ raw) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps_total = (uint64_t) gridDim.x * (blockDim.x >> 5);
+    for (uint64_t h = (uint64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); h < n; h += warps_total) {
+        const bool skip_count = counts[h] != 0;
+        if (skip_count && raw == nullptr) continue;
+        const uint32_t id = ids[h];
+        const uint16_t dg = diags[h];
+        const int d = (int) (int16_t) dg;
+        const int dist1 = (uint16_t) (0 - dg), dist2 = dg;
+        const int mind = min(dist1, dist2);
+        const int tl = len[id];
+        int qoff = 0, toff = 0, cells = 0;
+        if (d >= 0 && mind < qlen) { qoff = mind; cells = min(tl, qlen - mind); }
+        else if (d < 0 && mind < tl) { toff = mind; cells = min(tl - mind, qlen); }
+        const uint8_t *t = db + off[id] + toff;
+        const int chunk = (cells + 31) >> 5;
+        const int s0 = lane * chunk, s1 = min(cells, s0 + chunk);
+        Seg sg = {0, 0, 0, 0};
+        int cur = 0;
+        for (int p = s0; p < s1; p++) {
+            const int v = prof[(size_t) t[p] * qlen + qoff + p];
+            sg.sum += v;
+            sg.pre = max(sg.pre, sg.sum);
+            cur = max(0, cur + v);
+            sg.best = max(sg.best, cur);
+        }
+        sg.suf = cur;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            Seg r;
+            r.sum = __shfl_down_sync(0xffffffffu, sg.sum, o);
+            r.pre = __shfl_down_sync(0xffffffffu, sg.pre, o);
+            r.suf = __shfl_down_sync(0xffffffffu, sg.suf, o);
+            r.best = __shfl_down_sync(0xffffffffu, sg.best, o);
+            if ((lane & (2 * o - 1)) == 0) sg = seg_combine(sg, r);
+        }
+        if (lane == 0) {
+            if (raw) raw[h] = sg.best;
+            if (!skip_count) counts[h] = (uint8_t) min(255, sg.best);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// padded device profiles for the gapped kernel: [(A+1)][Lp] int8, rows >= qlen and residue row A = -128.
+// The reversed copy (prof_rev[a][r] = prof[a][qlen-1-r]) serves the start-position pass, which the reference runs
+// on query_rev_sequence / composition_bias_rev (StripedSmithWaterman.cpp:1150-1175).
+// ------------------------------------------------------------------------------------------------
+__global__ void pad_profile_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict__ qd, int A,
+                                   int8_t *__restrict__ padded) {
+    const QueryDesc q = qd[blockIdx.x];
+    const int8_t *src = raw + q.raw_off;
+    int8_t *fwd = padded + q.pad_off;
+    int8_t *rev = padded + q.rev_off;
+    const int total = (A + 1) * q.Lp;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int a = idx / q.Lp, j = idx % q.Lp;
+        int8_t f = -128, r = -128;
+        if (a < A && j < q.qlen) { f = src[(size_t) a * q.qlen + j]; r = src[(size_t) a * q.qlen + (q.qlen - 1 - j)]; }
+        fwd[idx] = f;
+        rev[idx] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// A3-A5: affine-gap local alignment, one warp per (query,target) pair, exact int32.
+// Reference semantics (re-verified by tests/test_oracle_vs_ref.py): textbook Gotoh
+//   H = max(0, Hdiag + s, E, F);  E' = max(E - ge, H - go);  F' = max(F - ge, H - go)
+// (sw_sse2_byte StripedSmithWaterman.cpp:98-299, sw_sse2_word :301-476); end column = first column at which the
+// running maximum reaches its final value, end row = smallest row holding it in that column (:233-247, :263-271).
+// DIR=-1 runs the same recurrence on the reversed prefixes query[qEnd..0] x target[dbEnd..0] and stops at the first
+// column whose maximum equals the forward score (alignStartPosBacktrace :1129-1212, `terminate` :259,:435).
+//
+// Lane l owns ROWS consecutive query rows of the current 32*ROWS-row tile and trails lane l-1 by one column; H and F
+// of the boundary row travel by __shfl_up.  Query tiles beyond the first pick their top boundary up from a per-warp
+// scratch row written by the previous tile.  Profile bytes come from shared memory (staged with a 1-D bulk/TMA copy)
+// or, for very long queries, straight from global memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int SW_ROWS = 8;
+constexpr int SW_TILE = 32 * SW_ROWS;
+constexpr int SW_WARPS = 4;
+
+template <int DIR>
+__global__ void __launch_bounds__(SW_WARPS * 32)
+sw32_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd, const WorkItem *__restrict__ items,
+            const PairDesc *__restrict__ pairs, const uint8_t *__restrict__ db, const uint64_t *__restrict__ off,
+            const int32_t *__restrict__ len, int A, int go, int ge, int2 *__restrict__ bnd, int bnd_stride,
+            int smem_profile, unsigned n_items, unsigned *__restrict__ item_counter, int4 *__restrict__ out) {
+    extern __shared__ __align__(16) int8_t smem_prof[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ unsigned next_pair;
+    __shared__ unsigned cur_item;
+
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
+    int2 *bnd0 = bnd + (size_t) warp_global * 2 * bnd_stride;
+    int2 *bnd1 = bnd0 + bnd_stride;
+    const int neg_ge = -ge;
+    unsigned phase = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+
+  // persistent CTA: items (<= kPairsPerItem pairs of one query, heaviest first) are handed out by a global counter
+  while (true) {
+    __syncthreads();  // everyone is done with the previous item's profile and next_pair
+    if (threadIdx.x == 0) cur_item = atomicAdd(item_counter, 1u);
+    __syncthreads();
+    const unsigned item_idx = cur_item;
+    if (item_idx >= n_items) break;
+    const WorkItem item = items[item_idx];
+    const QueryDesc q = qd[item.query];
+    const int8_t *gprof = padded + (DIR > 0 ? q.pad_off : q.rev_off);
+    const int Lp = q.Lp;
+    const int8_t *prof = gprof;
+    if (threadIdx.x == 0) next_pair = item.p0;
+    if (smem_profile) {
+        const unsigned bytes = (unsigned) ((A + 1) * Lp);  // Lp % 16 == 0
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, bytes);
+            for (unsigned o = 0; o < bytes; o += 32768u) bulk_g2s(smem_prof + o, gprof + o, min(32768u, bytes - o), &bar);
+        }
+        __syncthreads();
+        mbar_wait(&bar, phase);
+        phase ^= 1u;
+        prof = smem_prof;
+    } else {
+        __syncthreads();
+    }
+
+    while (true) {
+        unsigned p = 0;
+        if (lane == 0) p = atomicAdd(&next_pair, 1u);
+        p = __shfl_sync(0xffffffffu, p, 0);
+        if (p >= item.p1) break;
+        const PairDesc pd = pairs[p];
+        const int tl = len[pd.target];
+        const uint8_t *tbase = db + off[pd.target];
+        int nrows, row0, ncols, target_score;
+        if (DIR > 0) { nrows = q.qlen; row0 = 0; ncols = tl; target_score = 0; }
+        else { nrows = pd.qend + 1; row0 = q.qlen - 1 - pd.qend; ncols = pd.dbend + 1; tbase += pd.dbend; target_score = pd.score; }
+
+        int gbest = 0, gcol = 0x7fffffff, grow = 0x7fffffff;
+        int col_limit = ncols;
+        const int tiles = (nrows + SW_TILE - 1) / SW_TILE;
+        for (int tile = 0; tile < tiles; tile++) {
+            const int8_t *pptr = prof + row0 + tile * SW_TILE + lane * SW_ROWS;
+            int2 *bnd_rd = (tile & 1) ? bnd0 : bnd1;
+            int2 *bnd_wr = (tile & 1) ? bnd1 : bnd0;
+            const bool write_bnd = tile + 1 < tiles;
+            int H[SW_ROWS], Hg[SW_ROWS], E[SW_ROWS];
+#pragma unroll
+            for (int j = 0; j < SW_ROWS; j++) { H[j] = 0; Hg[j] = -go; E[j] = 0; }
+            int lbest = 0, lcol = 0, lrow = 0;
+            int hlast = 0, fout = 0, hdiag_in = 0;
+            int res = A, tchunk = A;
+            int2 bchunk = make_int2(0, 0);
+            int stop_at = -1;
+            const int nsteps = col_limit + 31;
+            for (int step = 0; step < nsteps; step++) {
+                if ((step & 31) == 0) {
+                    const int c = step + lane;
+                    tchunk = (c < col_limit) ? (int) tbase[(ptrdiff_t) c * DIR] : A;
+                    if (tile > 0) bchunk = (c < col_limit) ? bnd_rd[c] : make_int2(0, 0);
+                }
+                const int r0 = __shfl_sync(0xffffffffu, tchunk, step & 31);
+                res = __shfl_up_sync(0xffffffffu, res, 1);
+                int hin = __shfl_up_sync(0xffffffffu, hlast, 1);
+                int fin = __shfl_up_sync(0xffffffffu, fout, 1);
+                if (tile > 0) {
+                    const int bh = __shfl_sync(0xffffffffu, bchunk.x, step & 31);
+                    const int bf = __shfl_sync(0xffffffffu, bchunk.y, step & 31);
+                    if (lane == 0) { hin = bh; fin = bf; }
+                } else if (lane == 0) { hin = 0; fin = 0; }
+                if (lane == 0) res = r0;
+                const int col = step - lane;
+                if (col >= 0 && col < col_limit) {
+                    const int8_t *pp = pptr + (size_t) res * Lp;
+                    int diag = hdiag_in, f = fin, cm = 0;
+#pragma unroll
+                    for (int j = 0; j < SW_ROWS; j++) {
+                        const int s = pp[j];
+                        const int e = __viaddmax_s32(E[j], neg_ge, Hg[j]);
+                        int h = __viaddmax_s32_relu(diag, s, e);
+                        h = max(h, f);
+                        diag = H[j];
+                        H[j] = h;
+                        E[j] = e;
+                        const int hg = h - go;
+                        Hg[j] = hg;
+                        f = __viaddmax_s32(f, neg_ge, hg);
+                        cm = max(cm, h);
+                    }
+                    hlast = H[SW_ROWS - 1];
+                    fout = f;
+                    if (write_bnd && lane == 31) bnd_wr[col] = make_int2(hlast, f);
+                    if (cm > lbest) {
+                        lbest = cm; lcol = col;
+                        int jr = SW_ROWS - 1;
+#pragma unroll
+                        for (int j = SW_ROWS - 2; j >= 0; j--) if (H[j] == cm) jr = j;
+                        lrow = tile * SW_TILE + lane * SW_ROWS + jr;
+                    }
+                }
+                hdiag_in = hin;
+                if (DIR < 0) {
+                    if (stop_at < 0 && __any_sync(0xffffffffu, lbest == target_score)) stop_at = step + 31;
+                    if (stop_at >= 0 && step >= stop_at) break;
+                }
+            }
+            // warp-wide lexicographic reduction: max score, then min column, then min row
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const int ob = __shfl_xor_sync(0xffffffffu, lbest, o);
+                const int oc = __shfl_xor_sync(0xffffffffu, lcol, o);
+                const int orow = __shfl_xor_sync(0xffffffffu, lrow, o);
+                if (ob > lbest || (ob == lbest && (oc < lcol || (oc == lcol && orow < lrow)))) { lbest = ob; lcol = oc; lrow = orow; }
+            }
+            if (lbest > gbest || (lbest == gbest && lbest > 0 && (lcol < gcol || (lcol == gcol && lrow < grow)))) {
+                gbest = lbest; gcol = lcol; grow = lrow;
+            }
+            if (DIR < 0 && gbest == target_score && gbest > 0) col_limit = min(col_limit, gcol + 1);
+            if (write_bnd) __syncwarp();
+        }
+        if (lane == 0) out[p] = (gbest > 0) ? make_int4(gbest, gcol, grow, 0) : make_int4(0, -1, -1, 0);
+    }
+  }
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+namespace {
+
+int set_err(b200_ctx *ctx, int code, const char *msg) { ctx->err = msg; return code; }
+
+struct ScanCfg { int G, K; };
+const ScanCfg kScanCfgs[] = {{8, 4}, {8, 8}, {8, 12}, {8, 16}, {16, 12}, {16, 16}, {16, 24}, {32, 16}, {32, 24}, {32, 32}};
+
+template <int G, int K>
+cudaError_t launch_scan_cfg(b200_ctx *ctx, const int8_t *raw, const QueryDesc *qd, int nq, uint8_t *dense) {
+    const size_t smem = (size_t) 2 * (ctx->alphabet + 1) * (K / 4) * G * sizeof(uint4);
+    cudaError_t e = cudaFuncSetAttribute(ungapped_scan_kernel<G, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ungapped_scan_kernel<G, K>, 256, smem);
+    if (e != cudaSuccess) return e;
+    per_sm = std::max(per_sm, 1);
+    const uint64_t groups_per_cta = 256 / G;
+    uint64_t ctas = (uint64_t) ctx->sm_count * per_sm;
+    ctas = std::max<uint64_t>(1, std::min<uint64_t>(ctas, (ctx->n_seq + groups_per_cta - 1) / groups_per_cta));
+    if (nq > 1) ctas = std::max<uint64_t>(1, (ctas + nq - 1) / nq);
+    dim3 grid((unsigned) ctas, (unsigned) nq);
+    ungapped_scan_kernel<G, K><<<grid, 256, smem, ctx->stream>>>(raw, qd, ctx->d_res, ctx->d_off, ctx->d_len, ctx->d_order,
+                                                               (uint32_t) ctx->n_seq, ctx->alphabet, dense);
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
+// queries of one launch must share a (G,K) configuration; the caller groups them by capacity class
+cudaError_t launch_scan(b200_ctx *ctx, int cfg, const int8_t *raw, const QueryDesc *qd, int nq, uint8_t *dense) {
+    switch (cfg) {
+        case 0: return launch_scan_cfg<8, 4>(ctx, raw, qd, nq, dense);
+        case 1: return launch_scan_cfg<8, 8>(ctx, raw, qd, nq, dense);
+        case 2: return launch_scan_cfg<8, 12>(ctx, raw, qd, nq, dense);
+        case 3: return launch_scan_cfg<8, 16>(ctx, raw, qd, nq, dense);
+        case 4: return launch_scan_cfg<16, 12>(ctx, raw, qd, nq, dense);
+        case 5: return launch_scan_cfg<16, 16>(ctx, raw, qd, nq, dense);
+        case 6: return launch_scan_cfg<16, 24>(ctx, raw, qd, nq, dense);
+        case 7: return launch_scan_cfg<32, 16>(ctx, raw, qd, nq, dense);
+        case 8: return launch_scan_cfg<32, 24>(ctx, raw, qd, nq, dense);
+        default: return launch_scan_cfg<32, 32>(ctx, raw, qd, nq, dense);
+    }
+}
+
+int scan_cfg_for(int qlen) {
+    const int n = (int) (sizeof(kScanCfgs) / sizeof(kScanCfgs[0]));
+    for (int i = 0; i < n; i++)
+        if (2 * kScanCfgs[i].G * kScanCfgs[i].K >= qlen + 1) return i;
+    return -1;
+}
+
+// stage raw profiles + descriptors for a set of queries; fills h_qd (pad offsets only when with_pad)
+int stage_queries(b200_ctx *ctx, const b200_query *queries, int nq, bool with_pad, std::vector<QueryDesc> &h_qd) {
+    const int A = ctx->alphabet;
+    h_qd.resize(nq);
+    uint64_t raw_bytes = 0, pad_bytes = 0;
+    for (int i = 0; i < nq; i++) {
+        if (queries[i].profile == nullptr || queries[i].qlen <= 0) return set_err(ctx, B200_ERR_ARG, "query without profile or qlen <= 0");
+        QueryDesc &d = h_qd[i];
+        d.qlen = queries[i].qlen;
+        d.bias = queries[i].bias;
+        d.raw_off = raw_bytes;
+        raw_bytes += round_up((uint64_t) A * d.qlen, 16);
+        d.Lp = (int) round_up((uint64_t) d.qlen, 16) + SW_TILE;
+        d.pad_off = pad_bytes;
+        d.rev_off = pad_bytes + (uint64_t) (A + 1) * d.Lp;
+        pad_bytes += 2 * (uint64_t) (A + 1) * d.Lp;
+        d.pad_ = 0;
+    }
+    std::vector<int8_t> h_raw(raw_bytes, 0);
+    for (int i = 0; i < nq; i++) memcpy(h_raw.data() + h_qd[i].raw_off, queries[i].profile, (size_t) A * h_qd[i].qlen);
+    CU_TRY(ctx, ctx->raw.reserve(raw_bytes));
+    CU_TRY(ctx, ctx->qdesc.reserve(sizeof(QueryDesc) * nq));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->raw.p, h_raw.data(), raw_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->qdesc.p, h_qd.data(), sizeof(QueryDesc) * nq, cudaMemcpyHostToDevice, ctx->stream));
+    if (with_pad) {
+        CU_TRY(ctx, ctx->pad.reserve(pad_bytes));
+        pad_profile_kernel<<<nq, 256, 0, ctx->stream>>>(ctx->raw.as<int8_t>(), ctx->qdesc.as<QueryDesc>(), A, ctx->pad.as<int8_t>());
+        ctx->launches++;
+        CU_TRY(ctx, cudaGetLastError());
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));  // h_raw goes out of scope
+    return B200_OK;
+}
+
+}  // namespace
+
+// ---- jobs ------------------------------------------------------------------------------------------
+struct b200_job {
+    b200_ctx *ctx = nullptr;
+    int kind = 0;  // 1 scan, 2 sw forward
+    uint64_t cells = 0;
+    // scan
+    int nq = 0, thr = 0;
+    uint32_t k = 0;
+    std::vector<int> cfg_of_query;             // per query
+    std::vector<std::vector<int>> cfg_groups;  // query indices per configuration (launch groups)
+    DevBuf raw, qdesc, qdesc_grouped, dense, hits, nhits, pad;
+    std::vector<int> grouped_order;  // position -> original query index
+    // sw
+    uint64_t n_pairs = 0;
+    int go = 0, ge = 0;
+    DevBuf pairs, items, out4, bnd;
+    uint32_t n_items = 0;
+    int bnd_stride = 0;
+    int smem_bytes = 0, smem_profile = 0;
+    std::vector<uint32_t> perm;        // sorted position -> caller index
+    std::vector<b200_pair> h_pairs;    // caller order
+    std::vector<int32_t> h_qlen, h_bias;
+    void free_all() {
+        raw.release(); qdesc.release(); qdesc_grouped.release(); dense.release(); hits.release(); nhits.release();
+        pad.release(); pairs.release(); items.release(); out4.release(); bnd.release();
+    }
+};
+
+// All b200_* functions below are declared extern "C" in include/b200_align.h and keep that linkage here.
+
+int b200_create(int device, b200_ctx **out) {
+    if (out == nullptr) return B200_ERR_ARG;
+    *out = nullptr;
+    b200_ctx *ctx = new b200_ctx();
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return B200_ERR_CUDA; }
+    for (int i = 0; i < 16; i++) cudaEventCreate(&ctx->ev[i]);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major; ctx->cc_minor = prop.minor;
+    ctx->hbm = prop.totalGlobalMem;
+    ctx->max_smem_optin = (int) prop.sharedMemPerBlockOptin;
+    *out = ctx;
+    return B200_OK;
+}
+
+static void db_free(b200_ctx *ctx) {
+    if (ctx->d_res) cudaFree(ctx->d_res);
+    if (ctx->d_off) cudaFree(ctx->d_off);
+    if (ctx->d_len) cudaFree(ctx->d_len);
+    if (ctx->d_order) cudaFree(ctx->d_order);
+    ctx->d_res = nullptr; ctx->d_off = nullptr; ctx->d_len = nullptr; ctx->d_order = nullptr;
+    ctx->n_seq = 0; ctx->n_res = 0;
+}
+
+void b200_destroy(b200_ctx *ctx) {
+    if (ctx == nullptr) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    db_free(ctx);
+    DevBuf *bufs[] = {&ctx->raw, &ctx->pad, &ctx->qdesc, &ctx->dense, &ctx->hits, &ctx->nhits, &ctx->pairs, &ctx->items,
+                      &ctx->out4, &ctx->bnd, &ctx->ids, &ctx->diags, &ctx->counts, &ctx->rawout, &ctx->counter};
+    for (DevBuf *b : bufs) b->release();
+    for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *b200_last_error(const b200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int b200_device_info(const b200_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, uint64_t *hbm_bytes) {
+    if (ctx == nullptr) return B200_ERR_ARG;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    if (hbm_bytes) *hbm_bytes = ctx->hbm;
+    return B200_OK;
+}
+
+uint64_t b200_launch_count(const b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int b200_event_record(b200_ctx *ctx, int slot) {
+    if (ctx == nullptr || slot < 0 || slot >= 16) return B200_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaEventRecord(ctx->ev[slot], ctx->stream));
+    return B200_OK;
+}
+
+int b200_event_elapsed_ms(b200_ctx *ctx, int a, int b, float *ms) {
+    if (ctx == nullptr || ms == nullptr || a < 0 || a >= 16 || b < 0 || b >= 16) return B200_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaEventSynchronize(ctx->ev[b]));
+    CU_TRY(ctx, cudaEventElapsedTime(ms, ctx->ev[a], ctx->ev[b]));
+    return B200_OK;
+}
+
+int b200_sync(b200_ctx *ctx) {
+    if (ctx == nullptr) return B200_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+// ---- DB -------------------------------------------------------------------------------------------
+int b200_db_load(b200_ctx *ctx, const uint8_t *residues, const uint64_t *offsets, uint64_t n_seq, int alphabet) {
+    if (ctx == nullptr) return B200_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (residues == nullptr || offsets == nullptr || n_seq == 0 || alphabet <= 0 || alphabet > 31)
+        return set_err(ctx, B200_ERR_ARG, "b200_db_load: bad arguments");
+    if (n_seq >= 0xffffffffull) return set_err(ctx, B200_ERR_RANGE, "b200_db_load: more than 2^32-1 sequences");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    db_free(ctx);
+    std::vector<uint64_t> h_off(n_seq);
+    ctx->h_len.resize(n_seq);
+    uint64_t total = 0;
+    int max_len = 0;
+    for (uint64_t i = 0; i < n_seq; i++) {
+        if (offsets[i + 1] < offsets[i]) return set_err(ctx, B200_ERR_ARG, "b200_db_load: offsets not monotone");
+        const uint64_t l = offsets[i + 1] - offsets[i];
+        if (l > 65535) return set_err(ctx, B200_ERR_RANGE, "b200_db_load: sequence longer than 65535 (maxSeqLen)");
+        h_off[i] = total;
+        ctx->h_len[i] = (int32_t) l;
+        max_len = std::max(max_len, (int) l);
+        total += round_up(l, 16);
+    }
+    total += 32;
+    std::vector<uint8_t> h_res(total, (uint8_t) alphabet);
+    for (uint64_t i = 0; i < n_seq; i++) {
+        const uint8_t *src = residues + offsets[i];
+        uint8_t *dst = h_res.data() + h_off[i];
+        for (int32_t j = 0; j < ctx->h_len[i]; j++) {
+            if (src[j] >= alphabet) return set_err(ctx, B200_ERR_ARG, "b200_db_load: residue code >= alphabet (strip the +32 mask bit first)");
+            dst[j] = src[j];
+        }
+    }
+    std::vector<uint32_t> order(n_seq);
+    std::iota(order.begin(), order.end(), 0u);
+    const int32_t *hl = ctx->h_len.data();
+    std::stable_sort(order.begin(), order.end(), [hl](uint32_t a, uint32_t b) { return hl[a] > hl[b]; });
+    CU_TRY(ctx, cudaMalloc(&ctx->d_res, total));
+    CU_TRY(ctx, cudaMalloc(&ctx->d_off, n_seq * sizeof(uint64_t)));
+    CU_TRY(ctx, cudaMalloc(&ctx->d_len, n_seq * sizeof(int32_t)));
+    CU_TRY(ctx, cudaMalloc(&ctx->d_order, n_seq * sizeof(uint32_t)));
+    CU_TRY(ctx, cudaMemcpy(ctx->d_res, h_res.data(), total, cudaMemcpyHostToDevice));
+    CU_TRY(ctx, cudaMemcpy(ctx->d_off, h_off.data(), n_seq * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    CU_TRY(ctx, cudaMemcpy(ctx->d_len, ctx->h_len.data(), n_seq * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CU_TRY(ctx, cudaMemcpy(ctx->d_order, order.data(), n_seq * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    ctx->n_seq = n_seq;
+    ctx->n_res = offsets[n_seq] - offsets[0];
+    ctx->alphabet = alphabet;
+    ctx->max_len = max_len;
+    return B200_OK;
+}
+
+uint64_t b200_db_num_seqs(const b200_ctx *ctx) { return ctx ? ctx->n_seq : 0; }
+uint64_t b200_db_num_residues(const b200_ctx *ctx) { return ctx ? ctx->n_res : 0; }
+
+// ---- A2 ---------------------------------------------------------------------------------------------
+int b200_scan_job_create(b200_ctx *ctx, const b200_query *queries, int nq, int min_score_excl, uint32_t max_hits,
+                         b200_job **out) {
+    if (ctx == nullptr || out == nullptr) return B200_ERR_ARG;
+    *out = nullptr;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->n_seq == 0) return set_err(ctx, B200_ERR_NODB, "no target DB loaded");
+    if (queries == nullptr || nq <= 0 || max_hits == 0) return set_err(ctx, B200_ERR_ARG, "b200_ungapped_scan: bad arguments");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const int A = ctx->alphabet;
+    // group queries by kernel configuration so that one launch covers one group (grid.y = group size)
+    std::vector<std::vector<int>> groups(sizeof(kScanCfgs) / sizeof(kScanCfgs[0]));
+    for (int i = 0; i < nq; i++) {
+        if (queries[i].profile == nullptr || queries[i].qlen <= 0) return set_err(ctx, B200_ERR_ARG, "query without profile");
+        if (queries[i].bias < 0 || queries[i].bias > 255) return set_err(ctx, B200_ERR_ARG, "profile bias outside [0,255]");
+        const int c = scan_cfg_for(queries[i].qlen);
+        if (c < 0) return set_err(ctx, B200_ERR_RANGE, "b200_ungapped_scan: query longer than 2047 residues is not supported yet");
+        groups[c].push_back(i);
+    }
+    b200_job *job = new b200_job();
+    job->ctx = ctx; job->kind = 1; job->nq = nq; job->thr = min_score_excl; job->k = max_hits;
+    job->cfg_groups = groups;
+    std::vector<QueryDesc> h_qd;
+    uint64_t raw_bytes = 0;
+    for (size_t c = 0; c < groups.size(); c++)
+        for (int qi : groups[c]) {
+            QueryDesc d;
+            memset(&d, 0, sizeof(d));
+            d.qlen = queries[qi].qlen; d.bias = queries[qi].bias; d.raw_off = raw_bytes;
+            raw_bytes += round_up((uint64_t) A * d.qlen, 16);
+            h_qd.push_back(d);
+            job->grouped_order.push_back(qi);
+            job->cells += (uint64_t) d.qlen * ctx->n_res;
+        }
+    std::vector<int8_t> h_raw(raw_bytes, 0);
+    for (int pos = 0; pos < nq; pos++)
+        memcpy(h_raw.data() + h_qd[pos].raw_off, queries[job->grouped_order[pos]].profile, (size_t) A * h_qd[pos].qlen);
+    cudaError_t e = job->raw.reserve(raw_bytes);
+    if (e == cudaSuccess) e = job->qdesc.reserve(sizeof(QueryDesc) * nq);
+    if (e == cudaSuccess) e = job->dense.reserve((size_t) nq * ctx->n_seq);
+    if (e == cudaSuccess) e = job->hits.reserve((size_t) nq * max_hits * sizeof(b200_hit));
+    if (e == cudaSuccess) e = job->nhits.reserve((size_t) nq * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(job->raw.p, h_raw.data(), raw_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(job->qdesc.p, h_qd.data(), sizeof(QueryDesc) * nq, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("scan job staging: ") + cudaGetErrorString(e);
+        job->free_all(); delete job;
+        return e == cudaErrorMemoryAllocation ? B200_ERR_NOMEM : B200_ERR_CUDA;
+    }
+    *out = job;
+    return B200_OK;
+}
+
+static int scan_job_run_locked(b200_job *job) {
+    b200_ctx *ctx = job->ctx;
+    int pos = 0;
+    for (size_t c = 0; c < job->cfg_groups.size(); c++) {
+        const int n = (int) job->cfg_groups[c].size();
+        if (n == 0) continue;
+        // grid.y is limited to 65535
+        for (int s = 0; s < n; s += 32768) {
+            const int m = std::min(32768, n - s);
+            CU_TRY(ctx, launch_scan(ctx, (int) c, job->raw.as<int8_t>(), job->qdesc.as<QueryDesc>() + pos + s, m,
+                                    job->dense.as<uint8_t>() + (size_t) (pos + s) * ctx->n_seq));
+        }
+        pos += n;
+    }
+    topk_select_kernel<<<job->nq, 1024, 0, ctx->stream>>>(job->dense.as<uint8_t>(), (uint32_t) ctx->n_seq, job->thr, job->k,
+                                                          job->hits.as<b200_hit>(), job->nhits.as<uint32_t>());
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    return B200_OK;
+}
+
+int b200_scan_job_fetch(b200_job *job, b200_hit *hits, uint32_t *n_hits, uint8_t *dense) {
+    if (job == nullptr || job->kind != 1) return B200_ERR_ARG;
+    b200_ctx *ctx = job->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const int nq = job->nq;
+    const uint32_t k = job->k;
+    std::vector<b200_hit> h_hits((size_t) nq * k);
+    std::vector<uint32_t> h_n(nq);
+    CU_TRY(ctx, cudaMemcpyAsync(h_n.data(), job->nhits.p, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(h_hits.data(), job->hits.p, sizeof(b200_hit) * nq * k, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dense != nullptr) {
+        for (int pos = 0; pos < nq; pos++)
+            CU_TRY(ctx, cudaMemcpyAsync(dense + (size_t) job->grouped_order[pos] * ctx->n_seq,
+                                        job->dense.as<uint8_t>() + (size_t) pos * ctx->n_seq, ctx->n_seq,
+                                        cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int pos = 0; pos < nq; pos++) {
+        const int qi = job->grouped_order[pos];
+        const uint32_t n = std::min(h_n[pos], k);
+        b200_hit *src = h_hits.data() + (size_t) pos * k;
+        std::sort(src, src + n, [](const b200_hit &a, const b200_hit &b) {
+            return a.score != b.score ? a.score > b.score : a.id < b.id;
+        });
+        if (hits) memcpy(hits + (size_t) qi * k, src, sizeof(b200_hit) * n);
+        if (n_hits) n_hits[qi] = n;
+    }
+    return B200_OK;
+}
+
+int b200_ungapped_scan(b200_ctx *ctx, const b200_query *queries, int nq, int min_score_excl, uint32_t max_hits,
+                       b200_hit *hits, uint32_t *n_hits, uint8_t *dense) {
+    b200_job *job = nullptr;
+    int rc = b200_scan_job_create(ctx, queries, nq, min_score_excl, max_hits, &job);
+    if (rc != B200_OK) return rc;
+    rc = b200_job_run(job);
+    if (rc == B200_OK) rc = b200_scan_job_fetch(job, hits, n_hits, dense);
+    b200_job_destroy(job);
+    return rc;
+}
+
+// ---- A1 ---------------------------------------------------------------------------------------------
+int b200_diag_score(b200_ctx *ctx, const b200_query *q, const uint32_t *ids, const uint16_t *diagonals, uint64_t n,
+                    uint8_t *counts, int32_t *raw) {
+    if (ctx == nullptr) return B200_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->n_seq == 0) return set_err(ctx, B200_ERR_NODB, "no target DB loaded");
+    if (q == nullptr || q->profile == nullptr || q->qlen <= 0 || ids == nullptr || diagonals == nullptr || counts == nullptr)
+        return set_err(ctx, B200_ERR_ARG, "b200_diag_score: bad arguments");
+    if (q->qlen >= 32768 || ctx->max_len >= 32768)
+        return set_err(ctx, B200_ERR_RANGE, "b200_diag_score: sequences >= 32768 take the reference's computeLongScore path (T6)");
+    if (n == 0) return B200_OK;
+    for (uint64_t i = 0; i < n; i++)
+        if (ids[i] >= ctx->n_seq) return set_err(ctx, B200_ERR_ARG, "b200_diag_score: target id out of range");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t pbytes = (size_t) ctx->alphabet * q->qlen;
+    CU_TRY(ctx, ctx->raw.reserve(pbytes));
+    CU_TRY(ctx, ctx->ids.reserve(n * sizeof(uint32_t)));
+    CU_TRY(ctx, ctx->diags.reserve(n * sizeof(uint16_t)));
+    CU_TRY(ctx, ctx->counts.reserve(n));
+    if (raw) CU_TRY(ctx, ctx->rawout.reserve(n * sizeof(int32_t)));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->raw.p, q->profile, pbytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->ids.p, ids, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->diags.p, diagonals, n * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->counts.p, counts, n, cudaMemcpyHostToDevice, ctx->stream));
+    const uint64_t warps = (n + 0) ;
+    const unsigned ctas = (unsigned) std::min<uint64_t>((warps + 7) / 8, (uint64_t) ctx->sm_count * 8);
+    diag_score_kernel<<<ctas, 256, 0, ctx->stream>>>(ctx->raw.as<int8_t>(), q->qlen, ctx->d_res, ctx->d_off, ctx->d_len,
+                                                     ctx->ids.as<uint32_t>(), ctx->diags.as<uint16_t>(), n,
+                                                     ctx->counts.as<uint8_t>(), raw ? ctx->rawout.as<int32_t>() : nullptr);
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    CU_TRY(ctx, cudaMemcpyAsync(counts, ctx->counts.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (raw) CU_TRY(ctx, cudaMemcpyAsync(raw, ctx->rawout.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+// ---- A3-A5 ------------------------------------------------------------------------------------------
+namespace {
+
+constexpr uint32_t kPairsPerItem = 32;
+
+struct SwPlan {
+    std::vector<uint32_t> perm;  // sorted position -> caller index
+    std::vector<WorkItem> items;
+};
+
+// sort pairs by (query, target length desc) and cut each query's run into CTA-sized items, longest work first
+void plan_pairs(const b200_ctx *ctx, const b200_query *queries, const b200_pair *pairs, uint64_t n, const uint8_t *mask, SwPlan &plan) {
+    std::vector<int32_t> qlens;
+    { uint32_t mq = 0; for (uint64_t i = 0; i < n; i++) mq = std::max(mq, pairs[i].query); qlens.resize((size_t) mq + 1); for (uint32_t i = 0; i <= mq; i++) qlens[i] = queries[i].qlen; }
+    plan.perm.clear();
+    plan.perm.reserve(n);
+    for (uint64_t i = 0; i < n; i++) if (mask == nullptr || mask[i]) plan.perm.push_back((uint32_t) i);
+    const int32_t *hl = ctx->h_len.data();
+    std::stable_sort(plan.perm.begin(), plan.perm.end(), [pairs, hl](uint32_t a, uint32_t b) {
+        if (pairs[a].query != pairs[b].query) return pairs[a].query < pairs[b].query;
+        return hl[pairs[a].target] > hl[pairs[b].target];
+    });
+    plan.items.clear();
+    const uint32_t m = (uint32_t) plan.perm.size();
+    uint32_t s = 0;
+    while (s < m) {
+        uint32_t e = s;
+        const uint32_t qy = pairs[plan.perm[s]].query;
+        while (e < m && pairs[plan.perm[e]].query == qy) e++;
+        for (uint32_t p = s; p < e; p += kPairsPerItem) {
+            WorkItem it; it.query = qy; it.p0 = p; it.p1 = std::min(e, p + kPairsPerItem); it.pad_ = 0;
+            plan.items.push_back(it);
+        }
+        s = e;
+    }
+    // heaviest items first (longest-processing-time order for the dynamic item counter)
+    std::vector<uint64_t> cost(plan.items.size());
+    for (size_t k = 0; k < plan.items.size(); k++) {
+        uint64_t c = 0;
+        for (uint32_t p = plan.items[k].p0; p < plan.items[k].p1; p++) c += (uint64_t) hl[pairs[plan.perm[p]].target];
+        cost[k] = c * (uint64_t) qlens[plan.items[k].query];
+    }
+    std::vector<uint32_t> io(plan.items.size());
+    std::iota(io.begin(), io.end(), 0u);
+    std::stable_sort(io.begin(), io.end(), [&cost](uint32_t a, uint32_t b) { return cost[a] > cost[b]; });
+    std::vector<WorkItem> sorted(plan.items.size());
+    for (size_t k = 0; k < io.size(); k++) sorted[k] = plan.items[io[k]];
+    plan.items.swap(sorted);
+}
+
+// resident CTAs of the gapped kernel for a given dynamic shared-memory size (also sizes the boundary scratch)
+template <int DIR>
+unsigned sw_grid(b200_ctx *ctx, size_t smem, unsigned n_items) {
+    int per_sm = 0;
+    cudaFuncSetAttribute(sw32_kernel<DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 1024));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw32_kernel<DIR>, SW_WARPS * 32, smem) != cudaSuccess) per_sm = 1;
+    per_sm = std::max(1, per_sm);
+    return (unsigned) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) ctx->sm_count * per_sm, n_items));
+}
+unsigned sw_max_grid(const b200_ctx *ctx) { return (unsigned) ctx->sm_count * 16u; }
+
+template <int DIR>
+int launch_sw(b200_ctx *ctx, const QueryDesc *d_qd, const int8_t *d_pad, int max_Lp, const WorkItem *d_items, uint32_t n_items,
+              const PairDesc *d_pairs, int go, int ge, int2 *d_bnd, int bnd_stride, int4 *d_out) {
+    const int A = ctx->alphabet;
+    size_t smem = (size_t) (A + 1) * max_Lp;
+    int smem_profile = 1;
+    if (smem > (size_t) ctx->max_smem_optin - 1024) { smem = 0; smem_profile = 0; }
+    CU_TRY(ctx, cudaFuncSetAttribute(sw32_kernel<DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 1024)));
+    CU_TRY(ctx, ctx->counter.reserve(sizeof(unsigned)));
+    CU_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(unsigned), ctx->stream));
+    const unsigned grid = sw_grid<DIR>(ctx, smem, n_items);
+    sw32_kernel<DIR><<<grid, SW_WARPS * 32, smem, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
+                                                                ctx->d_len, A, go, ge, d_bnd, bnd_stride, smem_profile, n_items,
+                                                                ctx->counter.as<unsigned>(), d_out);
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    return B200_OK;
+}
+
+int check_pairs(b200_ctx *ctx, const b200_query *queries, int nq, const b200_pair *pairs, uint64_t n, int go, int ge) {
+    if (ctx->n_seq == 0) return set_err(ctx, B200_ERR_NODB, "no target DB loaded");
+    if (queries == nullptr || nq <= 0 || (pairs == nullptr && n > 0)) return set_err(ctx, B200_ERR_ARG, "sw: bad arguments");
+    if (go < 0 || go > 255 || ge < 0 || ge > 255) return set_err(ctx, B200_ERR_ARG, "sw: gap penalties are uint8 in the reference");
+    if (n >= 0xffffffffull) return set_err(ctx, B200_ERR_RANGE, "sw: more than 2^32-1 pairs in one call");
+    for (uint64_t i = 0; i < n; i++)
+        if (pairs[i].query >= (uint32_t) nq || pairs[i].target >= ctx->n_seq) return set_err(ctx, B200_ERR_ARG, "sw: pair index out of range");
+    return B200_OK;
+}
+
+// shared body: one direction over a planned set of pairs; results (score, col, row) come back in caller order
+template <int DIR>
+int run_sw_pass(b200_ctx *ctx, const std::vector<QueryDesc> &h_qd, const b200_pair *pairs, const SwPlan &plan,
+                const b200_sw_end *ends, int go, int ge, std::vector<int4> &res_sorted) {
+    const uint32_t m = (uint32_t) plan.perm.size();
+    res_sorted.assign(m, make_int4(0, -1, -1, 0));
+    if (m == 0) return B200_OK;
+    std::vector<PairDesc> h_pd(m);
+    int max_cols = 1;
+    for (uint32_t s = 0; s < m; s++) {
+        const uint32_t i = plan.perm[s];
+        PairDesc &d = h_pd[s];
+        d.target = pairs[i].target;
+        d.qend = d.dbend = d.score = 0;
+        if (DIR < 0) { d.qend = ends[i].qend; d.dbend = ends[i].dbend; d.score = ends[i].score; max_cols = std::max(max_cols, d.dbend + 1); }
+        else max_cols = std::max(max_cols, ctx->h_len[d.target]);
+    }
+    int max_Lp = 0;
+    bool multi = false;
+    for (const WorkItem &it : plan.items) {
+        max_Lp = std::max(max_Lp, h_qd[it.query].Lp);
+        if (h_qd[it.query].qlen > SW_TILE) multi = true;
+    }
+    const uint32_t n_items = (uint32_t) plan.items.size();
+    const int bnd_stride = multi ? (int) round_up((uint64_t) max_cols, 32) + 32 : 32;
+    CU_TRY(ctx, ctx->pairs.reserve(sizeof(PairDesc) * m));
+    CU_TRY(ctx, ctx->items.reserve(sizeof(WorkItem) * n_items));
+    CU_TRY(ctx, ctx->out4.reserve(sizeof(int4) * m));
+    CU_TRY(ctx, ctx->bnd.reserve(sizeof(int2) * 2 * (size_t) bnd_stride * std::min<uint64_t>(n_items, sw_max_grid(ctx)) * SW_WARPS));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->pairs.p, h_pd.data(), sizeof(PairDesc) * m, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->items.p, plan.items.data(), sizeof(WorkItem) * n_items, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_sw<DIR>(ctx, ctx->qdesc.as<QueryDesc>(), ctx->pad.as<int8_t>(), max_Lp, ctx->items.as<WorkItem>(), n_items,
+                            ctx->pairs.as<PairDesc>(), go, ge, ctx->bnd.as<int2>(), bnd_stride, ctx->out4.as<int4>());
+    if (rc != B200_OK) return rc;
+    CU_TRY(ctx, cudaMemcpyAsync(res_sorted.data(), ctx->out4.p, sizeof(int4) * m, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+// byte/word reporting rules of alignScoreEndPos (StripedSmithWaterman.cpp:892-941, T4/T5)
+inline void report_end(const int4 &r, int bias, b200_sw_end &o) {
+    const int score = r.x;
+    if (score + bias >= 255) {
+        o.score = std::min(score, 32767); o.qend = r.z; o.dbend = r.y; o.word = 1;
+    } else if (score == 0) {
+        o.score = 0; o.qend = 0; o.dbend = -1; o.word = 0;
+    } else {
+        o.score = score; o.qend = r.z; o.dbend = r.y; o.word = 0;
+    }
+}
+
+}  // namespace
+
+int b200_sw_score_endpos(b200_ctx *ctx, const b200_query *queries, int nq, const b200_pair *pairs, uint64_t n, int go,
+                         int ge, b200_sw_end *out) {
+    if (ctx == nullptr) return B200_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_pairs(ctx, queries, nq, pairs, n, go, ge);
+    if (rc != B200_OK) return rc;
+    if (n == 0) return B200_OK;
+    if (out == nullptr) return set_err(ctx, B200_ERR_ARG, "sw: out is NULL");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<QueryDesc> h_qd;
+    rc = stage_queries(ctx, queries, nq, true, h_qd);
+    if (rc != B200_OK) return rc;
+    SwPlan plan;
+    plan_pairs(ctx, queries, pairs, n, nullptr, plan);
+    std::vector<int4> res;
+    rc = run_sw_pass<1>(ctx, h_qd, pairs, plan, nullptr, go, ge, res);
+    if (rc != B200_OK) return rc;
+    for (uint32_t s = 0; s < plan.perm.size(); s++) {
+        const uint32_t i = plan.perm[s];
+        report_end(res[s], queries[pairs[i].query].bias, out[i]);
+    }
+    return B200_OK;
+}
+
+static int sw_startpos_locked(b200_ctx *ctx, const b200_query *queries, const std::vector<QueryDesc> &h_qd, const b200_pair *pairs, uint64_t n, int go,
+                              int ge, const b200_sw_end *ends, const uint8_t *gate, b200_sw_aln *out) {
+    std::vector<uint8_t> mask(n);
+    for (uint64_t i = 0; i < n; i++) {
+        out[i].score = ends[i].score; out[i].qend = ends[i].qend; out[i].dbend = ends[i].dbend; out[i].word = ends[i].word;
+        out[i].qstart = -1; out[i].dbstart = -1;
+        mask[i] = (ends[i].dbend != -1 && (gate == nullptr || gate[i])) ? 1 : 0;
+        if (mask[i]) {
+            const int ql = h_qd[pairs[i].query].qlen, tl = ctx->h_len[pairs[i].target];
+            if (ends[i].qend < 0 || ends[i].qend >= ql || ends[i].dbend < 0 || ends[i].dbend >= tl || ends[i].score <= 0)
+                return set_err(ctx, B200_ERR_ARG, "sw_startpos: end positions outside the sequences");
+        }
+    }
+    SwPlan plan;
+    plan_pairs(ctx, queries, pairs, n, mask.data(), plan);
+    std::vector<int4> res;
+    int rc = run_sw_pass<-1>(ctx, h_qd, pairs, plan, ends, go, ge, res);
+    if (rc != B200_OK) return rc;
+    for (uint32_t s = 0; s < plan.perm.size(); s++) {
+        const uint32_t i = plan.perm[s];
+        if (res[s].x != ends[i].score) return set_err(ctx, B200_ERR_ARG, "sw_startpos: reverse pass did not reproduce the forward score");
+        out[i].dbstart = ends[i].dbend - res[s].y;
+        out[i].qstart = ends[i].qend - res[s].z;
+    }
+    return B200_OK;
+}
+
+int b200_sw_startpos(b200_ctx *ctx, const b200_query *queries, int nq, const b200_pair *pairs, uint64_t n, int go, int ge,
+                     const b200_sw_end *ends, b200_sw_aln *out) {
+    if (ctx == nullptr) return B200_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_pairs(ctx, queries, nq, pairs, n, go, ge);
+    if (rc != B200_OK) return rc;
+    if (n == 0) return B200_OK;
+    if (ends == nullptr || out == nullptr) return set_err(ctx, B200_ERR_ARG, "sw_startpos: NULL argument");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<QueryDesc> h_qd;
+    rc = stage_queries(ctx, queries, nq, true, h_qd);
+    if (rc != B200_OK) return rc;
+    return sw_startpos_locked(ctx, queries, h_qd, pairs, n, go, ge, ends, nullptr, out);
+}
+
+int b200_sw_align(b200_ctx *ctx, const b200_query *queries, int nq, const b200_pair *pairs, uint64_t n, int go, int ge,
+                  const uint8_t *gate, b200_sw_aln *out) {
+    if (ctx == nullptr) return B200_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_pairs(ctx, queries, nq, pairs, n, go, ge);
+    if (rc != B200_OK) return rc;
+    if (n == 0) return B200_OK;
+    if (out == nullptr) return set_err(ctx, B200_ERR_ARG, "sw: out is NULL");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<QueryDesc> h_qd;
+    rc = stage_queries(ctx, queries, nq, true, h_qd);
+    if (rc != B200_OK) return rc;
+    SwPlan plan;
+    plan_pairs(ctx, queries, pairs, n, nullptr, plan);
+    std::vector<int4> res;
+    rc = run_sw_pass<1>(ctx, h_qd, pairs, plan, nullptr, go, ge, res);
+    if (rc != B200_OK) return rc;
+    std::vector<b200_sw_end> ends(n);
+    for (uint32_t s = 0; s < plan.perm.size(); s++) {
+        const uint32_t i = plan.perm[s];
+        report_end(res[s], queries[pairs[i].query].bias, ends[i]);
+    }
+    return sw_startpos_locked(ctx, queries, h_qd, pairs, n, go, ge, ends.data(), gate, out);
+}
+
+// ---- resident SW job (forward score + end positions) -----------------------------------------------------
+int b200_sw_job_create(b200_ctx *ctx, const b200_query *queries, int nq, const b200_pair *pairs, uint64_t n, int go, int ge,
+                       b200_job **out) {
+    if (ctx == nullptr || out == nullptr) return B200_ERR_ARG;
+    *out = nullptr;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_pairs(ctx, queries, nq, pairs, n, go, ge);
+    if (rc != B200_OK) return rc;
+    if (n == 0) return set_err(ctx, B200_ERR_ARG, "sw job: no pairs");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<QueryDesc> h_qd;
+    rc = stage_queries(ctx, queries, nq, true, h_qd);  // fills ctx->raw/qdesc/pad; the job takes copies below
+    if (rc != B200_OK) return rc;
+    b200_job *job = new b200_job();
+    job->ctx = ctx; job->kind = 2; job->go = go; job->ge = ge; job->n_pairs = n; job->nq = nq;
+    SwPlan plan;
+    plan_pairs(ctx, queries, pairs, n, nullptr, plan);
+    job->perm = plan.perm;
+    job->h_pairs.assign(pairs, pairs + n);
+    job->h_qlen.resize(nq); job->h_bias.resize(nq);
+    for (int i = 0; i < nq; i++) { job->h_qlen[i] = queries[i].qlen; job->h_bias[i] = queries[i].bias; }
+    std::vector<PairDesc> h_pd(n);
+    int max_cols = 1, max_Lp = 0;
+    bool multi = false;
+    for (uint32_t s = 0; s < n; s++) {
+        const uint32_t i = plan.perm[s];
+        h_pd[s].target = pairs[i].target; h_pd[s].qend = h_pd[s].dbend = h_pd[s].score = 0;
+        max_cols = std::max(max_cols, ctx->h_len[pairs[i].target]);
+        job->cells += (uint64_t) queries[pairs[i].query].qlen * (uint64_t) ctx->h_len[pairs[i].target];
+    }
+    for (const WorkItem &it : plan.items) {
+        max_Lp = std::max(max_Lp, h_qd[it.query].Lp);
+        if (h_qd[it.query].qlen > SW_TILE) multi = true;
+    }
+    job->n_items = (uint32_t) plan.items.size();
+    job->bnd_stride = multi ? (int) round_up((uint64_t) max_cols, 32) + 32 : 32;
+    job->smem_bytes = max_Lp;
+    const size_t pad_bytes = h_qd.back().rev_off + (size_t) (ctx->alphabet + 1) * h_qd.back().Lp;
+    cudaError_t e = job->pad.reserve(pad_bytes);
+    if (e == cudaSuccess) e = job->qdesc.reserve(sizeof(QueryDesc) * nq);
+    if (e == cudaSuccess) e = job->pairs.reserve(sizeof(PairDesc) * n);
+    if (e == cudaSuccess) e = job->items.reserve(sizeof(WorkItem) * job->n_items);
+    if (e == cudaSuccess) e = job->out4.reserve(sizeof(int4) * n);
+    if (e == cudaSuccess) e = job->bnd.reserve(sizeof(int2) * 2 * (size_t) job->bnd_stride * std::min<uint64_t>(job->n_items, sw_max_grid(ctx)) * SW_WARPS);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(job->pad.p, ctx->pad.p, pad_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(job->qdesc.p, h_qd.data(), sizeof(QueryDesc) * nq, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(job->pairs.p, h_pd.data(), sizeof(PairDesc) * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(job->items.p, plan.items.data(), sizeof(WorkItem) * job->n_items, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("sw job staging: ") + cudaGetErrorString(e);
+        job->free_all(); delete job;
+        return e == cudaErrorMemoryAllocation ? B200_ERR_NOMEM : B200_ERR_CUDA;
+    }
+    *out = job;
+    return B200_OK;
+}
+
+int b200_job_run(b200_job *job) {
+    if (job == nullptr) return B200_ERR_ARG;
+    b200_ctx *ctx = job->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    if (job->kind == 1) return scan_job_run_locked(job);
+    if (job->kind == 2)
+        return launch_sw<1>(ctx, job->qdesc.as<QueryDesc>(), job->pad.as<int8_t>(), job->smem_bytes, job->items.as<WorkItem>(),
+                            job->n_items, job->pairs.as<PairDesc>(), job->go, job->ge, job->bnd.as<int2>(), job->bnd_stride,
+                            job->out4.as<int4>());
+    return B200_ERR_ARG;
+}
+
+int b200_sw_job_fetch(b200_job *job, b200_sw_end *out) {
+    if (job == nullptr || job->kind != 2 || out == nullptr) return B200_ERR_ARG;
+    b200_ctx *ctx = job->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<int4> res(job->n_pairs);
+    CU_TRY(ctx, cudaMemcpyAsync(res.data(), job->out4.p, sizeof(int4) * job->n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint32_t s = 0; s < job->n_pairs; s++) {
+        const uint32_t i = job->perm[s];
+        report_end(res[s], job->h_bias[job->h_pairs[i].query], out[i]);
+    }
+    return B200_OK;
+}
+
+uint64_t b200_job_cells(const b200_job *job) { return job ? job->cells : 0; }
+
+void b200_job_destroy(b200_job *job) {
+    if (job == nullptr) return;
+    {
+        std::lock_guard<std::mutex> lk(job->ctx->mu);
+        cudaSetDevice(job->ctx->device);
+        cudaStreamSynchronize(job->ctx->stream);
+        job->free_all();
+    }
+    delete job;
+}
+

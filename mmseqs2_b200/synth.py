@@ -1,0 +1,65 @@
+"""Synthetic protein data of the BASELINE shapes: i.i.d. residues from the BLOSUM62 background,
+log-normal or normal lengths, planted mutated homologs.  numpy only; seeds are explicit so every rank / test / bench
+run regenerates identical bytes."""
+import numpy as np
+
+
+def background(pback):
+    p = np.array(pback[:20], np.float64)  # X excluded (prob 1e-5 in the matrix file -> 0 here)
+    return p / p.sum()
+
+
+def random_seqs(rng, n, bg, mean=300.0, sigma=0.6, lo=30, hi=5000, normal=False):
+    """-> (residues uint8 concatenated, offsets uint64[n+1])"""
+    if normal:
+        lens = np.clip(np.rint(rng.normal(mean, sigma, n)), lo, hi).astype(np.int64)
+    else:
+        lens = np.clip(np.rint(rng.lognormal(np.log(mean), sigma, n)), lo, hi).astype(np.int64)
+    off = np.zeros(n + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    total = int(off[-1])
+    cdf = np.cumsum(bg)
+    res = np.searchsorted(cdf, rng.random(total), side="right").astype(np.uint8)
+    np.minimum(res, 19, out=res)
+    return res, off
+
+
+def mutate(rng, seq, bg, subst=0.3, indel=0.02):
+    """copy of seq with substitutions and short indels"""
+    out = []
+    cdf = np.cumsum(bg)
+    for r in seq:
+        u = rng.random()
+        if u < indel / 2:
+            continue
+        if u < indel:
+            k = int(rng.integers(1, 6))
+            out.extend(np.minimum(np.searchsorted(cdf, rng.random(k), side="right"), 19).tolist())
+        if rng.random() < subst:
+            out.append(int(min(np.searchsorted(cdf, rng.random(), side="right"), 19)))
+        else:
+            out.append(int(r))
+    if not out:
+        out = [int(seq[0])]
+    return np.array(out, np.uint8)
+
+
+def plant_homologs(rng, res, off, queries, bg, frac=0.01, subst=0.3, indel=0.02):
+    """overwrite a window of ~frac of the targets with a mutated copy of a random query segment (in place)"""
+    n = len(off) - 1
+    k = max(1, int(n * frac))
+    ids = rng.choice(n, size=k, replace=False)
+    for t in ids:
+        q = queries[int(rng.integers(0, len(queries)))]
+        a = int(rng.integers(0, max(1, len(q) - 20)))
+        b = int(rng.integers(a + 10, len(q) + 1)) if len(q) > a + 10 else len(q)
+        m = mutate(rng, q[a:b], bg, subst, indel)
+        tl = int(off[t + 1] - off[t])
+        m = m[:tl]
+        s = int(rng.integers(0, tl - len(m) + 1))
+        res[int(off[t]) + s:int(off[t]) + s + len(m)] = m
+    return ids
+
+
+def split(res, off):
+    return [res[int(off[i]):int(off[i + 1])] for i in range(len(off) - 1)]

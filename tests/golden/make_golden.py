@@ -1,0 +1,70 @@
+"""tests/golden/make_golden.py -- regenerate the committed fixtures from the REFERENCE's own code.
+
+Runs only in the build container (needs oracle/_ref/libmmseqs_ref.so, i.e. /root/reference):
+    python tests/golden/make_golden.py
+Writes tests/golden/blosum62.npz (integer matrix at bitFactor 2, background, alphabet) and
+tests/golden/hotpath_v1.npz (seeded inputs + the reference outputs for A1, A2, A3-A5).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle.pyoracle import Ref, pack_targets  # noqa: E402
+from mmseqs2_b200 import synth  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    ref = Ref()
+    mat, pb, n2a = ref.matrix()
+    nmat, npb, nn2a = ref.matrix(nucl=True)
+    np.savez_compressed(os.path.join(HERE, "blosum62.npz"), mat=mat, pback=pb, alphabet=np.frombuffer(n2a.encode(), np.uint8),
+                        nucl_mat=nmat, nucl_pback=npb, nucl_alphabet=np.frombuffer(nn2a.encode(), np.uint8))
+    rng = np.random.default_rng(20260922)
+    bg = synth.background(pb)
+    out = {}
+    qlens = [1, 7, 33, 64, 65, 150, 255, 256, 257, 350, 511, 700, 1030]
+    queries = [synth.random_seqs(rng, 1, bg, mean=L, sigma=0, lo=L, hi=L, normal=True)[0] for L in qlens]
+    # X residues in a few queries
+    queries[3][::7] = 20
+    res, off = synth.random_seqs(rng, 400, bg, mean=250, sigma=0.7, lo=1, hi=1500)
+    synth.plant_homologs(rng, res, off, [q for q in queries if len(q) > 30], bg, frac=0.5, subst=0.25, indel=0.04)
+    # a near-identical long pair to force word mode, and targets starting with X
+    tg = synth.split(res.copy(), off)
+    tg[0] = queries[-1].copy()
+    tg[1] = synth.mutate(rng, queries[-2], bg, 0.1, 0.02)
+    tg[2] = np.concatenate([np.full(3, 20, np.uint8), tg[2]])
+    td, to = pack_targets(tg)
+    out["tdata"], out["toff"] = td, to
+    out["nq"] = np.array(len(queries))
+    for qi, q in enumerate(queries):
+        out["q%d" % qi] = q
+        for cbf in (0, 1):
+            key = "q%d_cb%d_" % (qi, cbf)
+            out[key + "ungapped"] = ref.ungapped(q, cbf, td, to)
+            out[key + "endpos"] = ref.sw_score_endpos(q, cbf, td, to)
+            aln, ev, _ = ref.ssw_align(q, cbf, td, to, mode=1)
+            out[key + "align"] = aln[:, :6]
+        # per-diagonal scorer
+        nh = 1500
+        ids = rng.integers(0, len(tg), nh).astype(np.uint32)
+        dg = rng.integers(-len(q) - 5, 600, nh).astype(np.int16).view(np.uint16)
+        ids[:6] = [0, 1, 0, 1, 0, 1]          # the planted (near-)identical targets: exercises the 255 clamp (T2)
+        dg[:6] = np.array([0, 0, 1, -1, -2, 3], np.int16).view(np.uint16)
+        f = ref.comp_bias(q)
+        out["q%d_diag_ids" % qi], out["q%d_diag_dg" % qi] = ids, dg
+        for cbf in (0, 1):
+            c, r = ref.diag(q, f if cbf else None, td, to, ids, dg)
+            out["q%d_cb%d_diag_counts" % (qi, cbf)] = c
+            out["q%d_cb%d_diag_raw" % (qi, cbf)] = r
+        out["q%d_compbias" % qi] = f
+    np.savez_compressed(os.path.join(HERE, "hotpath_v1.npz"), **out)
+    print("wrote fixtures:", {k: os.path.getsize(os.path.join(HERE, k)) for k in ("blosum62.npz", "hotpath_v1.npz")})
+
+
+if __name__ == "__main__":
+    main()

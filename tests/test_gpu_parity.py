@@ -1,0 +1,196 @@
+"""GPU (-m gpu): the CUDA path through the C ABI against (1) the committed reference outputs, (2) the oracle on seeded
+inputs, (3) size-independent properties at larger sizes.  Bit-exact everywhere (integer path)."""
+import numpy as np
+import pytest
+
+from mmseqs2_b200 import synth
+from oracle.pyoracle import pack_targets
+
+pytestmark = pytest.mark.gpu
+
+
+def _queries(golden):
+    return [golden["q%d" % i] for i in range(int(golden["nq"]))]
+
+
+def _expected_hits(dense, thr, k):
+    ids = np.nonzero(dense > thr)[0]
+    order = np.lexsort((ids, -dense[ids].astype(np.int64)))
+    ids = ids[order][:k]
+    return ids.astype(np.uint32), dense[ids].astype(np.int32)
+
+
+@pytest.fixture(scope="module")
+def golden_db(ctx, golden):
+    ctx.load_db(golden["tdata"], golden["toff"].astype(np.uint64), 21)
+    return golden["tdata"], golden["toff"]
+
+
+def test_scan_matches_reference_outputs(ctx, golden, golden_db, submat):
+    qs = _queries(golden)
+    for cbf in (0, 1):
+        profs = [submat.ssw_query(q, comp_bias=bool(cbf)) for q in qs]
+        hits, n_hits, dense = ctx.ungapped_scan(profs, min_score_excl=15, max_hits=50, want_dense=True)
+        for i in range(len(qs)):
+            exp = golden["q%d_cb%d_ungapped" % (i, cbf)]
+            assert np.array_equal(dense[i].astype(np.int32), exp), (i, cbf)
+            eid, esc = _expected_hits(exp, 15, 50)
+            assert n_hits[i] == len(eid)
+            assert np.array_equal(hits[i]["id"][:len(eid)], eid) and np.array_equal(hits[i]["score"][:len(eid)], esc)
+
+
+def test_sw_matches_reference_outputs(ctx, golden, golden_db, submat):
+    qs = _queries(golden)
+    n = len(golden["toff"]) - 1
+    pairs = np.array([(qi, t) for qi in range(len(qs)) for t in range(n)], np.uint32)
+    for cbf in (0, 1):
+        profs = [submat.ssw_query(q, comp_bias=bool(cbf)) for q in qs]
+        ends = ctx.sw_score_endpos(profs, pairs)
+        aln = ctx.sw_align(profs, pairs)
+        for qi in range(len(qs)):
+            e = golden["q%d_cb%d_endpos" % (qi, cbf)]
+            a = golden["q%d_cb%d_align" % (qi, cbf)]
+            sl = slice(qi * n, (qi + 1) * n)
+            got_e = np.stack([ends["score"][sl], ends["qend"][sl], ends["dbend"][sl], ends["word"][sl]], 1)
+            assert np.array_equal(got_e, e), (qi, cbf, np.nonzero((got_e != e).any(1))[0][:5])
+            got_a = np.stack([aln[f][sl] for f in ("score", "qstart", "qend", "dbstart", "dbend", "word")], 1)
+            assert np.array_equal(got_a, a), (qi, cbf, np.nonzero((got_a != a).any(1))[0][:5])
+
+
+def test_diag_matches_reference_outputs(ctx, golden, golden_db, submat):
+    for qi, q in enumerate(_queries(golden)):
+        ids, dg = golden["q%d_diag_ids" % qi], golden["q%d_diag_dg" % qi]
+        for cbf in (0, 1):
+            prof = submat.diag_query(q, golden["q%d_compbias" % qi] if cbf else None)
+            cnt, raw = ctx.diag_score(prof, ids, dg, want_raw=True)
+            assert np.array_equal(cnt, golden["q%d_cb%d_diag_counts" % (qi, cbf)]), (qi, cbf)
+            assert np.array_equal(raw, golden["q%d_cb%d_diag_raw" % (qi, cbf)]), (qi, cbf)
+    # entries with a non-zero count on input are left alone (UngappedAlignment.cpp:327-329)
+    q = _queries(golden)[5]
+    ids, dg = golden["q5_diag_ids"], golden["q5_diag_dg"]
+    pre = np.zeros(len(ids), np.uint8)
+    pre[::3] = 7
+    cnt, _ = ctx.diag_score(submat.diag_query(q, None), ids, dg, counts=pre)
+    exp = golden["q5_cb0_diag_counts"].copy()
+    exp[::3] = 7
+    assert np.array_equal(cnt, exp)
+
+
+@pytest.mark.parametrize("seed", [5, 6])
+def test_seeded_random_vs_oracle(ctx, oracle, submat, blosum, seed):
+    rng = np.random.default_rng(seed)
+    bg = synth.background(blosum[1])
+    res, off = synth.random_seqs(rng, 600, bg, mean=220, sigma=0.8, lo=1, hi=3000)
+    qlens = [3, 40, 127, 128, 129, 300, 511, 512, 513, 900, 2047]
+    qs = [synth.random_seqs(rng, 1, bg, mean=L, sigma=0, lo=L, hi=L, normal=True)[0] for L in qlens]
+    synth.plant_homologs(rng, res, off, [q for q in qs if len(q) > 30], bg, frac=0.4, subst=0.2, indel=0.03)
+    td, to = res, off.astype(np.int64)
+    ctx.load_db(td, off, 21)
+    profs = [submat.ssw_query(q) for q in qs]
+    _, _, dense = ctx.ungapped_scan(profs, want_dense=True)
+    n = len(off) - 1
+    pairs = np.array([(qi, t) for qi in range(len(qs)) for t in rng.choice(n, 150, replace=False)], np.uint32)
+    aln = ctx.sw_align(profs, pairs)
+    for qi, q in enumerate(qs):
+        cb, bias = oracle.query_cb(q, True)
+        assert np.array_equal(dense[qi].astype(np.int32), oracle.ungapped(q, cb, bias, td, to)), qi
+        sel = np.nonzero(pairs[:, 0] == qi)[0]
+        tg = [td[int(to[t]):int(to[t + 1])] for t in pairs[sel, 1]]
+        sd, so = pack_targets(tg)
+        exp = oracle.sw_align(q, cb, bias, sd, so)
+        got = np.stack([aln[f][sel] for f in ("score", "qstart", "qend", "dbstart", "dbend", "word")], 1)
+        assert np.array_equal(got, exp), (qi, np.nonzero((got != exp).any(1))[0][:5])
+
+
+def test_long_query_tiles_and_gap_variants(ctx, oracle, submat, blosum):
+    rng = np.random.default_rng(77)
+    bg = synth.background(blosum[1])
+    q = synth.random_seqs(rng, 1, bg, mean=2600, sigma=0, lo=2600, hi=2600, normal=True)[0]
+    tg = [synth.mutate(rng, q, bg, 0.15, 0.02), synth.mutate(rng, q[300:2100], bg, 0.4, 0.05),
+          synth.random_seqs(rng, 1, bg, mean=3000, sigma=0, lo=3000, hi=3000, normal=True)[0], q.copy(), q[:5].copy()]
+    td, to = pack_targets(tg)
+    ctx.load_db(td, to.astype(np.uint64), 21)
+    prof = submat.ssw_query(q)
+    cb, bias = oracle.query_cb(q, True)
+    pairs = np.array([(0, t) for t in range(len(tg))], np.uint32)
+    for go, ge in ((11, 1), (5, 2), (20, 3)):
+        aln = ctx.sw_align([prof], pairs, go=go, ge=ge)
+        got = np.stack([aln[f] for f in ("score", "qstart", "qend", "dbstart", "dbend", "word")], 1)
+        assert np.array_equal(got, oracle.sw_align(q, cb, bias, td, to, go, ge)), (go, ge)
+
+
+def test_gate_and_passthrough(ctx, oracle, submat, blosum, golden, golden_db):
+    qs = _queries(golden)[4:7]
+    profs = [submat.ssw_query(q) for q in qs]
+    n = len(golden["toff"]) - 1
+    pairs = np.array([(qi, t) for qi in range(len(qs)) for t in range(0, n, 3)], np.uint32)
+    gate = (np.arange(len(pairs)) % 2).astype(np.uint8)
+    full = ctx.sw_align(profs, pairs)
+    gated = ctx.sw_align(profs, pairs, gate=gate)
+    for f in ("score", "qend", "dbend", "word"):
+        assert np.array_equal(full[f], gated[f])
+    on = gate == 1
+    assert np.array_equal(full["qstart"][on], gated["qstart"][on]) and np.array_equal(full["dbstart"][on], gated["dbstart"][on])
+    assert (gated["qstart"][~on] == -1).all() and (gated["dbstart"][~on] == -1).all()
+
+
+def test_properties_at_scale(ctx, submat, blosum):
+    """size-independent checks on a DB too big for the scalar oracle: permutation equivariance, run-to-run determinism,
+    symmetry of the gapped score without composition bias, self-alignment bounds."""
+    rng = np.random.default_rng(4242)
+    bg = synth.background(blosum[1])
+    res, off = synth.random_seqs(rng, 50000, bg, mean=300, sigma=0.6, lo=30, hi=5000)
+    qres, qoff = synth.random_seqs(rng, 6, bg, mean=350, sigma=35, lo=200, hi=500, normal=True)
+    qs = synth.split(qres, qoff)
+    synth.plant_homologs(rng, res, off, qs, bg, frac=0.01)
+    profs = [submat.ssw_query(q) for q in qs]
+    ctx.load_db(res, off, 21)
+    h1, n1, d1 = ctx.ungapped_scan(profs, want_dense=True)
+    job = ctx.scan_job(profs)
+    job.run(); job.run()
+    h2, n2, d2 = job.fetch(want_dense=True)
+    job.close()
+    assert np.array_equal(d1, d2) and np.array_equal(n1, n2) and np.array_equal(h1, h2)
+    assert int(d1.astype(np.int64).sum()) > 0
+    # permute the DB: dense scores must follow the permutation
+    n = len(off) - 1
+    perm = rng.permutation(n)
+    seqs = synth.split(res, off)
+    pres, poff = pack_targets([seqs[i] for i in perm])
+    ctx.load_db(pres, poff.astype(np.uint64), 21)
+    _, _, d3 = ctx.ungapped_scan(profs, want_dense=True)
+    assert np.array_equal(d3, d1[:, perm])
+    # gapped score symmetry score(q,t) == score(t,q) for a symmetric matrix without composition bias
+    sub = rng.choice(n, 300, replace=False)
+    tq = [submat.ssw_query(seqs[perm[i]], comp_bias=False) for i in sub[:20]]
+    qp = [submat.ssw_query(q, comp_bias=False) for q in qs]
+    fwd = ctx.sw_score_endpos(qp, np.array([(a, sub[b]) for a in range(len(qs)) for b in range(20)], np.uint32))
+    tdb, tdo = pack_targets(qs)
+    ctx.load_db(tdb, tdo.astype(np.uint64), 21)
+    bwd = ctx.sw_score_endpos(tq, np.array([(b, a) for a in range(len(qs)) for b in range(20)], np.uint32))
+    assert np.array_equal(fwd["score"], bwd["score"])
+    # self alignment: score == sum of diagonal scores, end = last residue, start = 0
+    selfp = ctx.sw_align(qp, np.array([(a, a) for a in range(len(qs))], np.uint32))
+    for a, q in enumerate(qs):
+        assert selfp["score"][a] == int(blosum[0][q, q].astype(np.int64).sum())
+        assert selfp["qend"][a] == len(q) - 1 and selfp["dbend"][a] == len(q) - 1
+        assert selfp["qstart"][a] == 0 and selfp["dbstart"][a] == 0
+
+
+def test_error_paths(ctx, submat, blosum):
+    from mmseqs2_b200 import B200Error
+    rng = np.random.default_rng(1)
+    bg = synth.background(blosum[1])
+    res, off = synth.random_seqs(rng, 10, bg, mean=50, sigma=0.1, lo=10, hi=100)
+    ctx.load_db(res, off, 21)
+    q = submat.ssw_query(res[:30])
+    with pytest.raises(B200Error):
+        ctx.sw_score_endpos([q], np.array([(0, 10)], np.uint32))   # target id out of range
+    with pytest.raises(B200Error):
+        ctx.sw_score_endpos([q], np.array([(1, 0)], np.uint32))    # query index out of range
+    bad = res.copy(); bad[3] = 40
+    with pytest.raises(B200Error):
+        ctx.load_db(bad, off, 21)                                   # masked (+32) residue must be stripped first
+    ctx.load_db(res, off, 21)
+    out = ctx.sw_score_endpos([q], np.zeros((0, 2), np.uint32))     # empty batch is fine
+    assert len(out) == 0

@@ -1,0 +1,52 @@
+"""CPU: host-side profile logic of the product (include/b200_host.h) against the oracle, and the C-ABI surface:
+libb200align.so loads and exports every symbol the headers declare (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200h?_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    names = _declared("b200_align.h") + _declared("b200_host.h")
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "missing export: " + n
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from mmseqs2_b200 import api
+    monkeypatch.setattr(api, "_LIB", None)
+    monkeypatch.setattr(api, "_HERE", str(tmp_path))
+    try:
+        api.load_library()
+    except api.B200Error as e:
+        assert "no CPU path" in str(e)
+    else:
+        raise AssertionError("expected B200Error")
+
+
+def test_host_profiles_match_oracle(golden, oracle, submat):
+    for i in range(int(golden["nq"])):
+        q = golden["q%d" % i]
+        f = submat.comp_bias(q)
+        assert np.array_equal(f.view(np.uint32), golden["q%d_compbias" % i].view(np.uint32))
+        for cbf in (True, False):
+            qp = submat.ssw_query(q, comp_bias=cbf)
+            cb, bias = oracle.query_cb(q, cbf)
+            assert qp.bias == bias and np.array_equal(qp.cb, cb)
+            exp = oracle.mat[:, q].astype(np.int32) + cb.astype(np.int32)[None, :]   # mat[a][q[j]] + cb[j]
+            assert np.array_equal(qp.profile.astype(np.int32), exp)
+        dq = submat.diag_query(q, f)
+        cb4 = oracle.round_bias_diag(f)
+        exp = oracle.mat[q, :].T.astype(np.int32) + cb4.astype(np.int32)[None, :]     # mat[q[j]][a] + cb4[j]
+        assert np.array_equal(dq.profile.astype(np.int32), exp)

@@ -1,0 +1,58 @@
+"""CPU: the C restatement (oracle/oracle.c) against the committed reference outputs (tests/golden/hotpath_v1.npz,
+generated from the reference's own code by tests/golden/make_golden.py)."""
+import numpy as np
+
+
+def _queries(golden):
+    return [golden["q%d" % i] for i in range(int(golden["nq"]))]
+
+
+def test_comp_bias_bits(golden, oracle):
+    for i, q in enumerate(_queries(golden)):
+        f = oracle.comp_bias(q)
+        assert np.array_equal(f.view(np.uint32), golden["q%d_compbias" % i].view(np.uint32))
+
+
+def test_ungapped_scan_scores(golden, oracle):
+    td, to = golden["tdata"], golden["toff"]
+    for i, q in enumerate(_queries(golden)):
+        for cbf in (0, 1):
+            cb, bias = oracle.query_cb(q, bool(cbf))
+            got = oracle.ungapped(q, cb, bias, td, to)
+            assert np.array_equal(got, golden["q%d_cb%d_ungapped" % (i, cbf)]), (i, cbf)
+
+
+def test_sw_score_endpos(golden, oracle):
+    td, to = golden["tdata"], golden["toff"]
+    words = 0
+    for i, q in enumerate(_queries(golden)):
+        for cbf in (0, 1):
+            cb, bias = oracle.query_cb(q, bool(cbf))
+            got = oracle.sw_score_endpos(q, cb, bias, td, to)
+            exp = golden["q%d_cb%d_endpos" % (i, cbf)]
+            assert np.array_equal(got, exp), (i, cbf)
+            words += int(exp[:, 3].sum())
+    assert words > 50  # the fixture exercises the byte->word promotion (T5)
+
+
+def test_sw_align_start_positions(golden, oracle):
+    td, to = golden["tdata"], golden["toff"]
+    for i, q in enumerate(_queries(golden)):
+        for cbf in (0, 1):
+            cb, bias = oracle.query_cb(q, bool(cbf))
+            got = oracle.sw_align(q, cb, bias, td, to)
+            assert np.array_equal(got, golden["q%d_cb%d_align" % (i, cbf)]), (i, cbf)
+
+
+def test_diag_scores(golden, oracle):
+    td, to = golden["tdata"], golden["toff"]
+    clamped = 0
+    for i, q in enumerate(_queries(golden)):
+        ids, dg = golden["q%d_diag_ids" % i], golden["q%d_diag_dg" % i]
+        for cbf in (0, 1):
+            cb4 = oracle.round_bias_diag(golden["q%d_compbias" % i]) if cbf else np.zeros(len(q), np.int8)
+            c, r = oracle.diag(q, cb4, td, to, ids, dg)
+            assert np.array_equal(c, golden["q%d_cb%d_diag_counts" % (i, cbf)]), (i, cbf)
+            assert np.array_equal(r, golden["q%d_cb%d_diag_raw" % (i, cbf)]), (i, cbf)
+            clamped += int((c == 255).sum())
+    assert clamped > 0  # 255 clamp exercised (T2)
