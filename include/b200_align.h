@@ -14,6 +14,7 @@
  *                           (src/prefiltering/ungappedprefilter.cpp:418-478); same role as Marv::scan (marv.h:47).
  *   b200_diag_score         UngappedAlignment::align / scoreSingelSequenceByCounterResult
  *                           (src/prefiltering/UngappedAlignment.cpp:36-42, 440-460).
+ *   b200_sw_score           the score of alignScoreEndPos (ALIGNMENT_MODE_SCORE_ONLY use, Matcher.cpp:62-144).
  *   b200_sw_score_endpos    SmithWaterman::alignScoreEndPos (StripedSmithWaterman.cpp:892-941).
  *   b200_sw_startpos        the reverse pass of SmithWaterman::alignStartPosBacktrace (:1129-1212).
  *   b200_sw_align           ssw_align alignment modes 0/1 (:831-890) with the E-value/coverage gate supplied
@@ -91,6 +92,11 @@ int b200_diag_score(b200_ctx *ctx, const b200_query *q, const uint32_t *ids, con
                     uint8_t *counts, int32_t *raw);
 
 /* ---- A3-A5: affine-gap local alignment --------------------------------------------------------- */
+/* score only (s_align.score1 as alignScoreEndPos reports it: exact, capped at 32767).  This is the fast path
+ * (two targets per warp in int16x2); Matcher-level callers run it on every prefilter hit, apply the reference's
+ * E-value gate on the host, and ask for positions (below) only for the survivors. */
+int b200_sw_score(b200_ctx *ctx, const b200_query *queries, int n_queries, const b200_pair *pairs, uint64_t n,
+                  int gap_open, int gap_extend, int32_t *scores);
 int b200_sw_score_endpos(b200_ctx *ctx, const b200_query *queries, int n_queries, const b200_pair *pairs, uint64_t n,
                          int gap_open, int gap_extend, b200_sw_end *out);
 /* ends[i] is the result of b200_sw_score_endpos for pairs[i]; pairs with ends[i].dbend == -1 are passed through */
@@ -105,9 +111,12 @@ int b200_scan_job_create(b200_ctx *ctx, const b200_query *queries, int n_queries
                          uint32_t max_hits, b200_job **job);
 int b200_sw_job_create(b200_ctx *ctx, const b200_query *queries, int n_queries, const b200_pair *pairs, uint64_t n,
                        int gap_open, int gap_extend, b200_job **job);
+int b200_sw_score_job_create(b200_ctx *ctx, const b200_query *queries, int n_queries, const b200_pair *pairs, uint64_t n,
+                             int gap_open, int gap_extend, b200_job **job);
 int b200_job_run(b200_job *job);                       /* enqueue on the ctx stream; does not synchronise */
 int b200_scan_job_fetch(b200_job *job, b200_hit *hits, uint32_t *n_hits, uint8_t *dense);
 int b200_sw_job_fetch(b200_job *job, b200_sw_end *out);
+int b200_sw_score_job_fetch(b200_job *job, int32_t *scores);
 uint64_t b200_job_cells(const b200_job *job);          /* sum over work items of qlen*tlen (GCUPS numerator) */
 void b200_job_destroy(b200_job *job);
 

@@ -149,6 +149,10 @@ class Job:
             dense = np.zeros((self.nq, ctx.n_seq), np.uint8) if want_dense else None
             ctx._check(ctx.lib.b200_scan_job_fetch(self.handle, _p(hits), _p(n_hits), _p(dense)))
             return hits, n_hits, dense
+        if self.kind == "sw_score":
+            out = np.zeros(self.n, np.int32)
+            ctx._check(ctx.lib.b200_sw_score_job_fetch(self.handle, _p(out)))
+            return out
         out = np.zeros(self.n, END_DTYPE)
         ctx._check(ctx.lib.b200_sw_job_fetch(self.handle, _p(out)))
         return out
@@ -263,6 +267,20 @@ class Context:
         out = np.zeros(len(pa), END_DTYPE)
         self._check(self.lib.b200_sw_score_endpos(self.h, cq, len(queries), _p(pa), _u64(len(pa)), go, ge, _p(out)))
         return out
+
+    def sw_score(self, queries, pairs, go=11, ge=1):
+        cq = _cqueries(queries)
+        pa = pairs if getattr(pairs, "dtype", None) == PAIR_DTYPE else self._pairs(pairs)
+        out = np.zeros(len(pa), np.int32)
+        self._check(self.lib.b200_sw_score(self.h, cq, len(queries), _p(pa), _u64(len(pa)), go, ge, _p(out)))
+        return out
+
+    def sw_score_job(self, queries, pairs, go=11, ge=1):
+        cq = _cqueries(queries)
+        pa = pairs if getattr(pairs, "dtype", None) == PAIR_DTYPE else self._pairs(pairs)
+        h = _vp()
+        self._check(self.lib.b200_sw_score_job_create(self.h, cq, len(queries), _p(pa), _u64(len(pa)), go, ge, ctypes.byref(h)))
+        return Job(self, h, "sw_score", n=len(pa))
 
     def sw_startpos(self, queries, pairs, ends, go=11, ge=1):
         cq = _cqueries(queries)

@@ -421,7 +421,7 @@ constexpr int SW_ROWS = 8;
 constexpr int SW_TILE = 32 * SW_ROWS;
 constexpr int SW_WARPS = 4;
 
-template <int DIR>
+template <int DIR, bool SMEM>
 __global__ void __launch_bounds__(SW_WARPS * 32)
 sw32_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd, const WorkItem *__restrict__ items,
             const PairDesc *__restrict__ pairs, const uint8_t *__restrict__ db, const uint64_t *__restrict__ off,
@@ -454,9 +454,8 @@ sw32_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd,
     const QueryDesc q = qd[item.query];
     const int8_t *gprof = padded + (DIR > 0 ? q.pad_off : q.rev_off);
     const int Lp = q.Lp;
-    const int8_t *prof = gprof;
     if (threadIdx.x == 0) next_pair = item.p0;
-    if (smem_profile) {
+    if (SMEM) {
         const unsigned bytes = (unsigned) ((A + 1) * Lp);  // Lp % 16 == 0
         if (threadIdx.x == 0) {
             mbar_expect_tx(&bar, bytes);
@@ -465,7 +464,6 @@ sw32_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd,
         __syncthreads();
         mbar_wait(&bar, phase);
         phase ^= 1u;
-        prof = smem_prof;
     } else {
         __syncthreads();
     }
@@ -486,7 +484,7 @@ sw32_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd,
         int col_limit = ncols;
         const int tiles = (nrows + SW_TILE - 1) / SW_TILE;
         for (int tile = 0; tile < tiles; tile++) {
-            const int8_t *pptr = prof + row0 + tile * SW_TILE + lane * SW_ROWS;
+            const int8_t *pptr = (SMEM ? (const int8_t *) smem_prof : gprof) + row0 + tile * SW_TILE + lane * SW_ROWS;
             int2 *bnd_rd = (tile & 1) ? bnd0 : bnd1;
             int2 *bnd_wr = (tile & 1) ? bnd1 : bnd0;
             const bool write_bnd = tile + 1 < tiles;
@@ -569,6 +567,171 @@ sw32_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// A3/A4 fast path: score-only affine-gap local DP, TWO targets of the same query per warp, packed in the halves of
+// int16x2 registers (DPX VIADDMNMX.S16x2 / VIMNMX3.S16x2).  Same recurrence as sw32_kernel; exact as long as no
+// cell exceeds int16 (the host routes pairs that could overflow to sw32_kernel).  The two targets sit on different
+// residues at any step, so their int8 profile bytes are fetched separately (vector LDS) and merged + sign-extended
+// into one packed score by a single PRMT (selector msb = sign replication).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+template <int K, bool SMEM>
+__global__ void __launch_bounds__(SW_WARPS * 32)
+sw16_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd, const WorkItem *__restrict__ items,
+            const PairDesc *__restrict__ pairs, const uint8_t *__restrict__ db, const uint64_t *__restrict__ off,
+            const int32_t *__restrict__ len, int A, int go, int ge, uint2 *__restrict__ bnd, int bnd_stride,
+            int smem_profile, unsigned n_items, unsigned *__restrict__ item_counter, int32_t *__restrict__ out) {
+    static_assert(K % 4 == 0 && K <= 16, "K in {4,8,12,16}");
+    constexpr int W = K / 4;
+    constexpr int TILE = 32 * K;
+    extern __shared__ __align__(16) int8_t smem_prof[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ unsigned next_pair;
+    __shared__ unsigned cur_item;
+
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
+    uint2 *bnd0 = bnd + (size_t) warp_global * 2 * bnd_stride;
+    uint2 *bnd1 = bnd0 + bnd_stride;
+    const uint32_t neg_ge2 = pack16(-ge, -ge), neg_go2 = pack16(-go, -go);
+    const uint32_t padres = (uint32_t) A | ((uint32_t) A << 8);
+    unsigned phase = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) cur_item = atomicAdd(item_counter, 1u);
+    __syncthreads();
+    const unsigned item_idx = cur_item;
+    if (item_idx >= n_items) break;
+    const WorkItem item = items[item_idx];
+    const QueryDesc q = qd[item.query];
+    const int8_t *gprof = padded + q.pad_off;
+    const int Lp = q.Lp;
+    if (threadIdx.x == 0) next_pair = item.p0;
+    if (SMEM) {
+        const unsigned bytes = (unsigned) ((A + 1) * Lp);
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, bytes);
+            for (unsigned o = 0; o < bytes; o += 32768u) bulk_g2s(smem_prof + o, gprof + o, min(32768u, bytes - o), &bar);
+        }
+        __syncthreads();
+        mbar_wait(&bar, phase);
+        phase ^= 1u;
+    } else {
+        __syncthreads();
+    }
+
+    while (true) {
+        unsigned p = 0;
+        if (lane == 0) p = atomicAdd(&next_pair, 2u);
+        p = __shfl_sync(0xffffffffu, p, 0);
+        if (p >= item.p1) break;
+        const bool has_b = p + 1 < item.p1;
+        const uint32_t ta = pairs[p].target, tb = has_b ? pairs[p + 1].target : ta;
+        const int tla = len[ta], tlb = has_b ? len[tb] : 0;
+        const uint8_t *pa_t = db + off[ta], *pb_t = db + off[tb];
+        const int ncols = max(tla, tlb);
+        const int tiles = (q.qlen + TILE - 1) / TILE;
+        uint32_t best = 0;
+        for (int tile = 0; tile < tiles; tile++) {
+            const int8_t *pptr = (SMEM ? (const int8_t *) smem_prof : gprof) + tile * TILE + lane * K;
+            uint2 *bnd_rd = (tile & 1) ? bnd0 : bnd1;
+            uint2 *bnd_wr = (tile & 1) ? bnd1 : bnd0;
+            const bool write_bnd = tile + 1 < tiles;
+            // State per row: H (previous column) and Eh = E + go.  F travels down the column as Fh = F + go.
+            // With go >= ge (host-checked) the recurrences become, per cell,
+            //   Eh' = max(Eh - ge, Hleft)            T = max(Hdiag + s, Eh' - go, 0)
+            //   H   = max(T, Fh - go)                Fh' = max(Fh - ge, T)
+            // all in place: a descending pass (E, T) then an ascending pass (F chain, one dependent op per row).
+            uint32_t H[K], Eh[K];
+#pragma unroll
+            for (int j = 0; j < K; j++) { H[j] = 0; Eh[j] = 0; }
+            uint32_t hlast = 0, fout = 0, hdiag_in = 0;
+            uint32_t res = padres, tchunk = padres;
+            uint2 bchunk = make_uint2(0, 0);
+            const int nsteps = ncols + 31;
+            for (int step = 0; step < nsteps; step++) {
+                if ((step & 31) == 0) {
+                    const int c = step + lane;
+                    const uint32_t ra = (c < tla) ? (uint32_t) pa_t[c] : (uint32_t) A;
+                    const uint32_t rb = (c < tlb) ? (uint32_t) pb_t[c] : (uint32_t) A;
+                    tchunk = ra | (rb << 8);
+                    if (tile > 0) bchunk = (c < ncols) ? bnd_rd[c] : make_uint2(0, 0);
+                }
+                const uint32_t r0 = __shfl_sync(0xffffffffu, tchunk, step & 31);
+                res = __shfl_up_sync(0xffffffffu, res, 1);
+                uint32_t hin = __shfl_up_sync(0xffffffffu, hlast, 1);
+                uint32_t fin = __shfl_up_sync(0xffffffffu, fout, 1);
+                if (tile > 0) {
+                    const uint32_t bh = __shfl_sync(0xffffffffu, bchunk.x, step & 31);
+                    const uint32_t bf = __shfl_sync(0xffffffffu, bchunk.y, step & 31);
+                    if (lane == 0) { hin = bh; fin = bf; }
+                } else if (lane == 0) { hin = 0; fin = 0; }
+                if (lane == 0) res = r0;
+                const int col = step - lane;
+                if (col >= 0 && col < ncols) {
+                    const int8_t *ppa = pptr + (size_t) (res & 0xffu) * Lp;
+                    const int8_t *ppb = pptr + (size_t) (res >> 8) * Lp;
+                    uint32_t wa[W], wb[W];
+                    if constexpr (K == 16) {
+                        const uint4 va = *reinterpret_cast<const uint4 *>(ppa), vb = *reinterpret_cast<const uint4 *>(ppb);
+                        wa[0] = va.x; wa[1] = va.y; wa[2] = va.z; wa[3] = va.w;
+                        wb[0] = vb.x; wb[1] = vb.y; wb[2] = vb.z; wb[3] = vb.w;
+                    } else if constexpr (K == 8) {
+                        const uint2 va = *reinterpret_cast<const uint2 *>(ppa), vb = *reinterpret_cast<const uint2 *>(ppb);
+                        wa[0] = va.x; wa[1] = va.y; wb[0] = vb.x; wb[1] = vb.y;
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < W; w++) {
+                            wa[w] = reinterpret_cast<const uint32_t *>(ppa)[w];
+                            wb[w] = reinterpret_cast<const uint32_t *>(ppb)[w];
+                        }
+                    }
+                    constexpr uint32_t SEL[4] = {0xC480u, 0xD591u, 0xE6A2u, 0xF7B3u};
+#pragma unroll
+                    for (int j = K - 1; j >= 0; j--) {
+                        const uint32_t sc = prmt_b32(wa[j >> 2], wb[j >> 2], SEL[j & 3]);
+                        Eh[j] = __viaddmax_s16x2(Eh[j], neg_ge2, H[j]);
+                        const uint32_t e = __vadd2(Eh[j], neg_go2);
+                        H[j] = __viaddmax_s16x2_relu(j > 0 ? H[j - 1] : hdiag_in, sc, e);
+                    }
+                    uint32_t f = fin;
+#pragma unroll
+                    for (int j = 0; j < K; j++) {
+                        const uint32_t fn = __viaddmax_s16x2(f, neg_ge2, H[j]);
+                        H[j] = __viaddmax_s16x2(f, neg_go2, H[j]);
+                        f = fn;
+                    }
+#pragma unroll
+                    for (int j = 0; j < K; j += 2) best = __vimax3_s16x2(best, H[j], H[j + 1]);
+                    hlast = H[K - 1];
+                    fout = f;
+                    if (write_bnd && lane == 31) bnd_wr[col] = make_uint2(hlast, f);
+                }
+                hdiag_in = hin;
+            }
+            if (write_bnd) __syncwarp();
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = __vmaxs2(best, __shfl_xor_sync(0xffffffffu, best, o));
+        if (lane == 0) {
+            out[p] = (int) (best & 0xffffu);
+            if (has_b) out[p + 1] = (int) (best >> 16);
+        }
+    }
+  }
+}
+
 // ================================================================================================
 // host side
 // ================================================================================================
@@ -634,7 +797,7 @@ int stage_queries(b200_ctx *ctx, const b200_query *queries, int nq, bool with_pa
         d.bias = queries[i].bias;
         d.raw_off = raw_bytes;
         raw_bytes += round_up((uint64_t) A * d.qlen, 16);
-        d.Lp = (int) round_up((uint64_t) d.qlen, 16) + SW_TILE;
+        d.Lp = (int) round_up((uint64_t) d.qlen, 128) + 512;
         d.pad_off = pad_bytes;
         d.rev_off = pad_bytes + (uint64_t) (A + 1) * d.Lp;
         pad_bytes += 2 * (uint64_t) (A + 1) * d.Lp;
@@ -680,7 +843,18 @@ struct b200_job {
     std::vector<uint32_t> perm;        // sorted position -> caller index
     std::vector<b200_pair> h_pairs;    // caller order
     std::vector<int32_t> h_qlen, h_bias;
+    // kind 3 (score-only): one part per kernel flavour (packed K in {4,8,12,16}, or 0 = int32 fallback)
+    struct Part {
+        int K = 0;
+        std::vector<uint32_t> perm;
+        DevBuf pairs, items, out;
+        uint32_t n_items = 0, n_pairs = 0;
+        int max_Lp = 0;
+    };
+    std::vector<Part *> parts;
     void free_all() {
+        for (Part *pt : parts) { pt->pairs.release(); pt->items.release(); pt->out.release(); delete pt; }
+        parts.clear();
         raw.release(); qdesc.release(); qdesc_grouped.release(); dense.release(); hits.release(); nhits.release();
         pad.release(); pairs.release(); items.release(); out4.release(); bnd.release();
     }
@@ -1029,8 +1203,10 @@ void plan_pairs(const b200_ctx *ctx, const b200_query *queries, const b200_pair 
 template <int DIR>
 unsigned sw_grid(b200_ctx *ctx, size_t smem, unsigned n_items) {
     int per_sm = 0;
-    cudaFuncSetAttribute(sw32_kernel<DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 1024));
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw32_kernel<DIR>, SW_WARPS * 32, smem) != cudaSuccess) per_sm = 1;
+    if (smem > 0) {
+        cudaFuncSetAttribute(sw32_kernel<DIR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw32_kernel<DIR, true>, SW_WARPS * 32, smem) != cudaSuccess) per_sm = 1;
+    } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw32_kernel<DIR, false>, SW_WARPS * 32, 0) != cudaSuccess) per_sm = 1;
     per_sm = std::max(1, per_sm);
     return (unsigned) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) ctx->sm_count * per_sm, n_items));
 }
@@ -1043,13 +1219,17 @@ int launch_sw(b200_ctx *ctx, const QueryDesc *d_qd, const int8_t *d_pad, int max
     size_t smem = (size_t) (A + 1) * max_Lp;
     int smem_profile = 1;
     if (smem > (size_t) ctx->max_smem_optin - 1024) { smem = 0; smem_profile = 0; }
-    CU_TRY(ctx, cudaFuncSetAttribute(sw32_kernel<DIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 1024)));
     CU_TRY(ctx, ctx->counter.reserve(sizeof(unsigned)));
     CU_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(unsigned), ctx->stream));
     const unsigned grid = sw_grid<DIR>(ctx, smem, n_items);
-    sw32_kernel<DIR><<<grid, SW_WARPS * 32, smem, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
-                                                                ctx->d_len, A, go, ge, d_bnd, bnd_stride, smem_profile, n_items,
-                                                                ctx->counter.as<unsigned>(), d_out);
+    if (smem_profile)
+        sw32_kernel<DIR, true><<<grid, SW_WARPS * 32, smem, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
+                                                                          ctx->d_len, A, go, ge, d_bnd, bnd_stride, smem_profile,
+                                                                          n_items, ctx->counter.as<unsigned>(), d_out);
+    else
+        sw32_kernel<DIR, false><<<grid, SW_WARPS * 32, 0, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
+                                                                        ctx->d_len, A, go, ge, d_bnd, bnd_stride, smem_profile,
+                                                                        n_items, ctx->counter.as<unsigned>(), d_out);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
     return B200_OK;
@@ -1267,12 +1447,210 @@ int b200_sw_job_create(b200_ctx *ctx, const b200_query *queries, int nq, const b
     return B200_OK;
 }
 
+
+// ---- score-only batch (packed int16x2 fast path + int32 fallback) ---------------------------------------------
+namespace {
+
+// rows per lane of the packed kernel for a query length: least padded rows, ties to the larger tile
+int sw16_k_for(int qlen) {
+    int bestK = 16;
+    long best_rows = -1;
+    const int ks[4] = {4, 8, 12, 16};
+    for (int i = 0; i < 4; i++) {
+        const long tile = 32L * ks[i];
+        const long rows = (qlen + tile - 1) / tile * tile;
+        const long tiles = rows / tile;
+        const long cost = rows + 40 * tiles;  // a tile restart costs about a 32-step pipeline fill
+        if (best_rows < 0 || cost <= best_rows) { best_rows = cost; bestK = ks[i]; }
+    }
+    return bestK;
+}
+
+template <int K>
+cudaError_t launch_sw16_k(b200_ctx *ctx, const QueryDesc *d_qd, const int8_t *d_pad, size_t smem, int smem_profile,
+                          const WorkItem *d_items, uint32_t n_items, const PairDesc *d_pairs, int go, int ge, uint2 *d_bnd,
+                          int bnd_stride, int32_t *d_out) {
+    int per_sm = 0;
+    if (smem_profile) {
+        cudaError_t e = cudaFuncSetAttribute(sw16_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+        if (e != cudaSuccess) return e;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw16_kernel<K, true>, SW_WARPS * 32, smem) != cudaSuccess) per_sm = 1;
+    } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw16_kernel<K, false>, SW_WARPS * 32, 0) != cudaSuccess) per_sm = 1;
+    per_sm = std::max(1, per_sm);
+    const unsigned grid = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) ctx->sm_count * per_sm, n_items));
+    if (smem_profile)
+        sw16_kernel<K, true><<<grid, SW_WARPS * 32, smem, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
+                                                                        ctx->d_len, ctx->alphabet, go, ge, d_bnd, bnd_stride,
+                                                                        smem_profile, n_items, ctx->counter.as<unsigned>(), d_out);
+    else
+        sw16_kernel<K, false><<<grid, SW_WARPS * 32, 0, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
+                                                                      ctx->d_len, ctx->alphabet, go, ge, d_bnd, bnd_stride,
+                                                                      smem_profile, n_items, ctx->counter.as<unsigned>(), d_out);
+    return cudaGetLastError();
+}
+
+int launch_sw16(b200_ctx *ctx, int K, const QueryDesc *d_qd, const int8_t *d_pad, int max_Lp, const WorkItem *d_items,
+                uint32_t n_items, const PairDesc *d_pairs, int go, int ge, uint2 *d_bnd, int bnd_stride, int32_t *d_out) {
+    size_t smem = (size_t) (ctx->alphabet + 1) * max_Lp;
+    int smem_profile = 1;
+    if (smem > (size_t) ctx->max_smem_optin - 1024) { smem = 0; smem_profile = 0; }
+    CU_TRY(ctx, ctx->counter.reserve(sizeof(unsigned)));
+    CU_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(unsigned), ctx->stream));
+    cudaError_t e;
+    switch (K) {
+        case 4: e = launch_sw16_k<4>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out); break;
+        case 8: e = launch_sw16_k<8>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out); break;
+        case 12: e = launch_sw16_k<12>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out); break;
+        default: e = launch_sw16_k<16>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out); break;
+    }
+    ctx->launches++;
+    CU_TRY(ctx, e);
+    return B200_OK;
+}
+
+}  // namespace
+
+int b200_sw_score_job_create(b200_ctx *ctx, const b200_query *queries, int nq, const b200_pair *pairs, uint64_t n, int go,
+                             int ge, b200_job **out) {
+    if (ctx == nullptr || out == nullptr) return B200_ERR_ARG;
+    *out = nullptr;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_pairs(ctx, queries, nq, pairs, n, go, ge);
+    if (rc != B200_OK) return rc;
+    if (n == 0) return set_err(ctx, B200_ERR_ARG, "sw score job: no pairs");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<QueryDesc> h_qd;
+    rc = stage_queries(ctx, queries, nq, true, h_qd);
+    if (rc != B200_OK) return rc;
+    const int A = ctx->alphabet;
+    // int16 safety: a local alignment cannot score more than min(qlen,tlen) * (largest profile entry)
+    std::vector<int> smax(nq, 1), kq(nq, 16);
+    for (int i = 0; i < nq; i++) {
+        int m = 1;
+        const int8_t *pr = queries[i].profile;
+        for (size_t k = 0; k < (size_t) A * queries[i].qlen; k++) m = std::max(m, (int) pr[k]);
+        smax[i] = m;
+        kq[i] = sw16_k_for(queries[i].qlen);
+    }
+    b200_job *job = new b200_job();
+    job->ctx = ctx; job->kind = 3; job->go = go; job->ge = ge; job->n_pairs = n; job->nq = nq;
+    const int klass[5] = {4, 8, 12, 16, 0};
+    std::vector<uint8_t> mask(n);
+    int max_cols = 1;
+    bool multi = false;
+    uint32_t max_items = 1;
+    cudaError_t e = cudaSuccess;
+    for (int c = 0; c < 5 && e == cudaSuccess; c++) {
+        bool any = false;
+        for (uint64_t i = 0; i < n; i++) {
+            const int qi = (int) pairs[i].query;
+            const int tl = ctx->h_len[pairs[i].target];
+            const bool packed_ok = go >= ge && (int64_t) std::min(queries[qi].qlen, tl) * smax[qi] < 32000;
+            const int k = packed_ok ? kq[qi] : 0;
+            mask[i] = (k == klass[c]) ? 1 : 0;
+            any |= mask[i] != 0;
+            if (c == 0) job->cells += (uint64_t) queries[qi].qlen * (uint64_t) tl;
+        }
+        if (!any) continue;
+        SwPlan plan;
+        plan_pairs(ctx, queries, pairs, n, mask.data(), plan);
+        b200_job::Part *pt = new b200_job::Part();
+        job->parts.push_back(pt);
+        pt->K = klass[c];
+        pt->perm = plan.perm;
+        pt->n_pairs = (uint32_t) plan.perm.size();
+        pt->n_items = (uint32_t) plan.items.size();
+        max_items = std::max(max_items, pt->n_items);
+        std::vector<PairDesc> h_pd(pt->n_pairs);
+        const int tile = klass[c] ? 32 * klass[c] : SW_TILE;
+        for (uint32_t sidx = 0; sidx < pt->n_pairs; sidx++) {
+            const uint32_t i = plan.perm[sidx];
+            h_pd[sidx].target = pairs[i].target; h_pd[sidx].qend = h_pd[sidx].dbend = h_pd[sidx].score = 0;
+            max_cols = std::max(max_cols, ctx->h_len[pairs[i].target]);
+            pt->max_Lp = std::max(pt->max_Lp, h_qd[pairs[i].query].Lp);
+            if (queries[pairs[i].query].qlen > tile) multi = true;
+        }
+        e = pt->pairs.reserve(sizeof(PairDesc) * pt->n_pairs);
+        if (e == cudaSuccess) e = pt->items.reserve(sizeof(WorkItem) * pt->n_items);
+        if (e == cudaSuccess) e = pt->out.reserve(sizeof(int4) * pt->n_pairs);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pt->pairs.p, h_pd.data(), sizeof(PairDesc) * pt->n_pairs, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pt->items.p, plan.items.data(), sizeof(WorkItem) * pt->n_items, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
+    job->bnd_stride = multi ? (int) round_up((uint64_t) max_cols, 32) + 32 : 32;
+    const size_t pad_bytes = h_qd.back().rev_off + (size_t) (A + 1) * h_qd.back().Lp;
+    if (e == cudaSuccess) e = job->pad.reserve(pad_bytes);
+    if (e == cudaSuccess) e = job->qdesc.reserve(sizeof(QueryDesc) * nq);
+    if (e == cudaSuccess) e = job->bnd.reserve(sizeof(int2) * 2 * (size_t) job->bnd_stride * std::min<uint64_t>(max_items, sw_max_grid(ctx)) * SW_WARPS);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(job->pad.p, ctx->pad.p, pad_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(job->qdesc.p, h_qd.data(), sizeof(QueryDesc) * nq, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("sw score job staging: ") + cudaGetErrorString(e);
+        job->free_all(); delete job;
+        return e == cudaErrorMemoryAllocation ? B200_ERR_NOMEM : B200_ERR_CUDA;
+    }
+    *out = job;
+    return B200_OK;
+}
+
+static int sw_score_job_run_locked(b200_job *job) {
+    b200_ctx *ctx = job->ctx;
+    for (b200_job::Part *pt : job->parts) {
+        int rc;
+        if (pt->K > 0)
+            rc = launch_sw16(ctx, pt->K, job->qdesc.as<QueryDesc>(), job->pad.as<int8_t>(), pt->max_Lp, pt->items.as<WorkItem>(),
+                             pt->n_items, pt->pairs.as<PairDesc>(), job->go, job->ge, job->bnd.as<uint2>(), job->bnd_stride,
+                             pt->out.as<int32_t>());
+        else
+            rc = launch_sw<1>(ctx, job->qdesc.as<QueryDesc>(), job->pad.as<int8_t>(), pt->max_Lp, pt->items.as<WorkItem>(),
+                              pt->n_items, pt->pairs.as<PairDesc>(), job->go, job->ge, job->bnd.as<int2>(), job->bnd_stride,
+                              pt->out.as<int4>());
+        if (rc != B200_OK) return rc;
+    }
+    return B200_OK;
+}
+
+int b200_sw_score_job_fetch(b200_job *job, int32_t *scores) {
+    if (job == nullptr || job->kind != 3 || scores == nullptr) return B200_ERR_ARG;
+    b200_ctx *ctx = job->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    for (b200_job::Part *pt : job->parts) {
+        if (pt->K > 0) {
+            std::vector<int32_t> h(pt->n_pairs);
+            CU_TRY(ctx, cudaMemcpyAsync(h.data(), pt->out.p, sizeof(int32_t) * pt->n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+            CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            for (uint32_t s = 0; s < pt->n_pairs; s++) scores[pt->perm[s]] = h[s];
+        } else {
+            std::vector<int4> h(pt->n_pairs);
+            CU_TRY(ctx, cudaMemcpyAsync(h.data(), pt->out.p, sizeof(int4) * pt->n_pairs, cudaMemcpyDeviceToHost, ctx->stream));
+            CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            for (uint32_t s = 0; s < pt->n_pairs; s++) scores[pt->perm[s]] = std::min(h[s].x, 32767);
+        }
+    }
+    return B200_OK;
+}
+
+int b200_sw_score(b200_ctx *ctx, const b200_query *queries, int nq, const b200_pair *pairs, uint64_t n, int go, int ge,
+                  int32_t *scores) {
+    if (n == 0) return (ctx == nullptr) ? B200_ERR_ARG : B200_OK;
+    b200_job *job = nullptr;
+    int rc = b200_sw_score_job_create(ctx, queries, nq, pairs, n, go, ge, &job);
+    if (rc != B200_OK) return rc;
+    rc = b200_job_run(job);
+    if (rc == B200_OK) rc = b200_sw_score_job_fetch(job, scores);
+    b200_job_destroy(job);
+    return rc;
+}
+
 int b200_job_run(b200_job *job) {
     if (job == nullptr) return B200_ERR_ARG;
     b200_ctx *ctx = job->ctx;
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     if (job->kind == 1) return scan_job_run_locked(job);
+    if (job->kind == 3) return sw_score_job_run_locked(job);
     if (job->kind == 2)
         return launch_sw<1>(ctx, job->qdesc.as<QueryDesc>(), job->pad.as<int8_t>(), job->smem_bytes, job->items.as<WorkItem>(),
                             job->n_items, job->pairs.as<PairDesc>(), job->go, job->ge, job->bnd.as<int2>(), job->bnd_stride,

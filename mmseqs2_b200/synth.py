@@ -25,23 +25,28 @@ def random_seqs(rng, n, bg, mean=300.0, sigma=0.6, lo=30, hi=5000, normal=False)
 
 
 def mutate(rng, seq, bg, subst=0.3, indel=0.02):
-    """copy of seq with substitutions and short indels"""
-    out = []
+    """copy of seq with substitutions and short indels (vectorised; deterministic for a given rng state)"""
+    seq = np.asarray(seq, np.uint8)
+    n = len(seq)
     cdf = np.cumsum(bg)
-    for r in seq:
-        u = rng.random()
-        if u < indel / 2:
-            continue
-        if u < indel:
-            k = int(rng.integers(1, 6))
-            out.extend(np.minimum(np.searchsorted(cdf, rng.random(k), side="right"), 19).tolist())
-        if rng.random() < subst:
-            out.append(int(min(np.searchsorted(cdf, rng.random(), side="right"), 19)))
-        else:
-            out.append(int(r))
-    if not out:
-        out = [int(seq[0])]
-    return np.array(out, np.uint8)
+    out = seq.copy()
+    sub = rng.random(n) < subst
+    out[sub] = np.minimum(np.searchsorted(cdf, rng.random(int(sub.sum())), side="right"), 19).astype(np.uint8)
+    u = rng.random(n)
+    keep = u >= indel / 2                      # deletions
+    ins_at = np.nonzero((u >= indel / 2) & (u < indel))[0]   # insertions before these positions
+    pieces = []
+    last = 0
+    for pos in ins_at:
+        pieces.append(out[last:pos][keep[last:pos]])
+        k = int(rng.integers(1, 6))
+        pieces.append(np.minimum(np.searchsorted(cdf, rng.random(k), side="right"), 19).astype(np.uint8))
+        last = pos
+    pieces.append(out[last:][keep[last:]])
+    res = np.concatenate(pieces) if pieces else out
+    if len(res) == 0:
+        res = seq[:1].copy()
+    return res.astype(np.uint8)
 
 
 def plant_homologs(rng, res, off, queries, bg, frac=0.01, subst=0.3, indel=0.02):
@@ -63,3 +68,12 @@ def plant_homologs(rng, res, off, queries, bg, frac=0.01, subst=0.3, indel=0.02)
 
 def split(res, off):
     return [res[int(off[i]):int(off[i + 1])] for i in range(len(off) - 1)]
+
+
+def pack(seqs):
+    """list of uint8 arrays -> (concatenated residues, uint64 offsets[n+1])"""
+    off = np.zeros(len(seqs) + 1, np.uint64)
+    if len(seqs):
+        off[1:] = np.cumsum([len(x) for x in seqs])
+    data = np.concatenate(seqs).astype(np.uint8) if len(seqs) else np.zeros(0, np.uint8)
+    return np.ascontiguousarray(data), off

@@ -20,7 +20,7 @@ def _expected_hits(dense, thr, k):
     return ids.astype(np.uint32), dense[ids].astype(np.int32)
 
 
-@pytest.fixture(scope="module")
+@pytest.fixture()
 def golden_db(ctx, golden):
     ctx.load_db(golden["tdata"], golden["toff"].astype(np.uint64), 21)
     return golden["tdata"], golden["toff"]
@@ -57,6 +57,29 @@ def test_sw_matches_reference_outputs(ctx, golden, golden_db, submat):
             assert np.array_equal(got_a, a), (qi, cbf, np.nonzero((got_a != a).any(1))[0][:5])
 
 
+def test_packed_score_matches_reference_outputs(ctx, golden, golden_db, submat):
+    """b200_sw_score (int16x2, two targets per warp) == score1 of alignScoreEndPos for every pair of the fixture"""
+    qs = _queries(golden)
+    n = len(golden["toff"]) - 1
+    pairs = np.array([(qi, t) for qi in range(len(qs)) for t in range(n)], np.uint32)
+    for cbf in (0, 1):
+        profs = [submat.ssw_query(q, comp_bias=bool(cbf)) for q in qs]
+        sc = ctx.sw_score(profs, pairs)
+        for qi in range(len(qs)):
+            exp = golden["q%d_cb%d_endpos" % (qi, cbf)][:, 0]
+            got = sc[qi * n:(qi + 1) * n]
+            assert np.array_equal(got, exp), (qi, cbf, np.nonzero(got != exp)[0][:5], got[got != exp][:5], exp[got != exp][:5])
+    # odd pair counts, single pairs, gap variants (go < ge takes the int32 kernel)
+    profs = [submat.ssw_query(q) for q in qs]
+    for go, ge in ((11, 1), (5, 2), (2, 3)):
+        sub = pairs[(pairs[:, 0] % 3 == 1)][:-1:7]
+        got = ctx.sw_score(profs, sub, go=go, ge=ge)
+        exp = ctx.sw_score_endpos(profs, sub, go=go, ge=ge)["score"]
+        assert np.array_equal(got, exp), (go, ge)
+    one = ctx.sw_score(profs, pairs[5:6])
+    assert one[0] == golden["q0_cb1_endpos"][5, 0]
+
+
 def test_diag_matches_reference_outputs(ctx, golden, golden_db, submat):
     for qi, q in enumerate(_queries(golden)):
         ids, dg = golden["q%d_diag_ids" % qi], golden["q%d_diag_dg" % qi]
@@ -91,6 +114,7 @@ def test_seeded_random_vs_oracle(ctx, oracle, submat, blosum, seed):
     n = len(off) - 1
     pairs = np.array([(qi, t) for qi in range(len(qs)) for t in rng.choice(n, 150, replace=False)], np.uint32)
     aln = ctx.sw_align(profs, pairs)
+    assert np.array_equal(ctx.sw_score(profs, pairs), aln["score"])
     for qi, q in enumerate(qs):
         cb, bias = oracle.query_cb(q, True)
         assert np.array_equal(dense[qi].astype(np.int32), oracle.ungapped(q, cb, bias, td, to)), qi
@@ -114,6 +138,7 @@ def test_long_query_tiles_and_gap_variants(ctx, oracle, submat, blosum):
     cb, bias = oracle.query_cb(q, True)
     pairs = np.array([(0, t) for t in range(len(tg))], np.uint32)
     for go, ge in ((11, 1), (5, 2), (20, 3)):
+        assert np.array_equal(ctx.sw_score([prof], pairs, go=go, ge=ge), oracle.sw_align(q, cb, bias, td, to, go, ge)[:, 0])
         aln = ctx.sw_align([prof], pairs, go=go, ge=ge)
         got = np.stack([aln[f] for f in ("score", "qstart", "qend", "dbstart", "dbend", "word")], 1)
         assert np.array_equal(got, oracle.sw_align(q, cb, bias, td, to, go, ge)), (go, ge)
