@@ -169,33 +169,43 @@ def cpu_reference_gcups(queries, res, off, budget_s, threads):
 
 
 def cpu_reference_sw(queries, td, to, pairs, budget_s, threads):
-    """alignScoreEndPos of the reference (or the port) over whole per-query target lists until the budget is spent"""
+    """alignScoreEndPos of the reference over a bounded prefix of the pair list, one OpenMP region over queries with one
+    SmithWaterman object per thread (the shape of Alignment::run); falls back to the C port when oracle/_ref is absent"""
     from oracle.pyoracle import Oracle, Ref
     mat, pb = load_matrix()
-    use_ref = Ref.available()
-    ref = Ref() if use_ref else None
-    orc = None if use_ref else Oracle(mat, pb)
     to64 = to.astype(np.int64)
-    cells, dt, nq = 0.0, 0.0, 0
-    order = np.argsort(pairs[:, 0], kind="stable")
-    qs = np.unique(pairs[:, 0])
-    for qi in qs:
-        if dt >= budget_s:
-            break
-        tl = pairs[order][pairs[order][:, 0] == qi][:, 1]
-        sd, so = td[int(to64[tl[0]]):int(to64[tl[-1] + 1])], to64[tl[0]:tl[-1] + 2] - to64[tl[0]]
-        q = queries[int(qi)]
+    cells_pair = np.array([len(queries[a]) * int(to64[b + 1] - to64[b]) for a, b in pairs], np.float64)
+    if Ref.available():
+        ref = Ref()
+        probe = pairs[pairs[:, 0] < 8]
         t0 = time.perf_counter()
-        if use_ref:
-            ref.sw_score_endpos(q, True, sd, so, nthreads=threads)
-        else:
-            cb, bias = orc.query_cb(q, True)
-            orc.sw_score_endpos(q, cb, bias, sd, so, nthreads=threads)
-        dt += time.perf_counter() - t0
-        cells += float(len(q)) * float(so[-1])
-        nq += 1
-    return {"value": cells / 1e9 / dt, "unit": METRIC, "cores": threads, "kind": "reference" if use_ref else "port",
-            "sample": "alignScoreEndPos, %d queries x their target lists = %.3g cells in %.1f s" % (nq, cells, dt)}
+        ref.sw_score_endpos_multi(queries, True, td, to64, probe, nthreads=threads)
+        dt0 = max(time.perf_counter() - t0, 1e-3)
+        rate = cells_pair[:len(probe)].sum() / dt0
+        nq = int(min(len(queries), max(threads, np.searchsorted(np.cumsum(cells_pair), rate * budget_s) // max(1, len(pairs) // len(queries)))))
+        sub = pairs[pairs[:, 0] < nq]
+        t0 = time.perf_counter()
+        ref.sw_score_endpos_multi(queries, True, td, to64, sub, nthreads=threads)
+        dt = time.perf_counter() - t0
+        cells = float(cells_pair[:len(sub)].sum())
+        kind = "reference"
+    else:
+        orc = Oracle(mat, pb)
+        cells, dt, nq = 0.0, 0.0, 0
+        for qi in range(len(queries)):
+            if dt >= budget_s:
+                break
+            tl = pairs[pairs[:, 0] == qi][:, 1]
+            sd, so = td[int(to64[tl[0]]):int(to64[tl[-1] + 1])], to64[tl[0]:tl[-1] + 2] - to64[tl[0]]
+            cb, bias = orc.query_cb(queries[qi], True)
+            t0 = time.perf_counter()
+            orc.sw_score_endpos(queries[qi], cb, bias, sd, so, nthreads=threads)
+            dt += time.perf_counter() - t0
+            cells += float(len(queries[qi])) * float(so[-1])
+            nq += 1
+        kind = "port"
+    return {"value": cells / 1e9 / dt, "unit": METRIC, "cores": threads, "kind": kind,
+            "sample": "alignScoreEndPos, first %d queries x their target lists = %.3g cells in %.1f s" % (nq, cells, dt)}
 
 
 def run_reference_arm(args):
@@ -291,18 +301,19 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def gather_hits(hits_np):
+    from mmseqs2_b200.sharding import gather_hit_lists
+
+    def gather_hits(hits_np, n_hits_np=None):
         if dist is None:
             return
-        t = torch.from_numpy(hits_np.view(np.int32).reshape(-1)).cuda()
-        outl = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(outl, t)
+        nh = n_hits_np if n_hits_np is not None else np.zeros(len(hits_np), np.uint32)
+        gather_hit_lists(hits_np, nh, args.queries_per_step, dist, device=torch.device("cuda", local_rank))
 
     # ---- value: resident inputs, device-timed -------------------------------------------------------
     for s in range(args.warmup):
         jobs[s % n_distinct].run()
         h, nh, _ = jobs[s % n_distinct].fetch()
-        gather_hits(h)
+        gather_hits(h, nh)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -316,7 +327,7 @@ def main():
         total_cells += cells_per_step[s % n_distinct]
         if dist is not None:
             h, nh, _ = j.fetch()
-            gather_hits(h)
+            gather_hits(h, nh)
     ctx.event_record(1)
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -338,7 +349,7 @@ def main():
     e2e_cells = 0
     for s in range(args.steps):
         h, nh, _ = ctx.ungapped_scan(batches[s % n_distinct], 15, args.max_hits)
-        gather_hits(h)
+        gather_hits(h, nh)
         e2e_cells += cells_per_step[s % n_distinct]
     barrier()
     e2e_s = time.perf_counter() - t0

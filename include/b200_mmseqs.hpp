@@ -1,0 +1,282 @@
+// include/b200_mmseqs.hpp -- host-side C++ mirror of the reference's operator surface, header-only, over the C ABI
+// (b200_align.h + b200_host.h).  C++11, no exceptions (MMseqs2 is built -fno-exceptions), no CUDA headers.
+//
+// The classes keep the reference's names, argument meaning and calling pattern so that the call sites in
+// ungappedprefilter.cpp / QueryMatcher.cpp / Alignment.cpp change by a type name and a batch boundary, not by logic:
+//
+//   b200::Marv               class Marv                      lib/libmarv/src/marv.h:6-58  (scan called at ungappedprefilter.cpp:207)
+//   b200::UngappedAlignment  class UngappedAlignment         src/prefiltering/UngappedAlignment.h:16-34  (QueryMatcher.cpp:119,131)
+//   b200::SmithWaterman      class SmithWaterman             src/alignment/StripedSmithWaterman.h:84-222 (Matcher.cpp:51-144)
+//
+// What differs, and why: the device wants many (query,target) pairs per call.  SmithWaterman therefore collects the
+// targets of one query (addTarget) and resolves them in one flush(); the E-value / coverage gate between "score",
+// "end position" and "start position" stays with the caller's EvalueComputation (host double math), expressed as a
+// callback, exactly where ssw_align_private applies it (StripedSmithWaterman.cpp:854-863).
+#ifndef B200_MMSEQS_HPP
+#define B200_MMSEQS_HPP
+
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "b200_align.h"
+#include "b200_host.h"
+
+namespace b200 {
+
+// One process-wide device context + resident DB (the role Marv's cudasw handle plays).
+class Device {
+public:
+    explicit Device(int deviceId = 0) : ctx_(NULL), status_(b200_create(deviceId, &ctx_)) {}
+    ~Device() { if (ctx_) b200_destroy(ctx_); }
+    bool ok() const { return status_ == B200_OK; }
+    int status() const { return status_; }
+    const char *error() const { return ctx_ ? b200_last_error(ctx_) : "b200_create failed"; }
+    b200_ctx *ctx() { return ctx_; }
+    // SequenceLookup layout (src/prefiltering/SequenceLookup.cpp:42-46): data + offsets[n+1]
+    int loadLookup(const unsigned char *data, const size_t *offsets, size_t nSeq, int alphabetSize) {
+        std::vector<uint64_t> off(nSeq + 1);
+        for (size_t i = 0; i <= nSeq; i++) off[i] = offsets[i];
+        return b200_db_load(ctx_, data, off.data(), nSeq, alphabetSize);
+    }
+private:
+    Device(const Device &);
+    Device &operator=(const Device &);
+    b200_ctx *ctx_;
+    int status_;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Marv: all-diagonals ungapped scan of one query profile against the resident DB.
+// ---------------------------------------------------------------------------------------------------------------
+class Marv {
+public:
+    enum AlignmentType { GAPLESS, SMITH_WATERMAN, GAPLESS_SMITH_WATERMAN };
+    struct Stats { size_t results; int numOverflows; double seconds; double gcups; };
+    struct Result {
+        unsigned int id; int score; int qEndPos; int dbEndPos;
+        Result() : id(0), score(0), qEndPos(0), dbEndPos(0) {}
+        Result(unsigned int id, int score, int qEndPos, int dbEndPos) : id(id), score(score), qEndPos(qEndPos), dbEndPos(dbEndPos) {}
+    };
+
+    Marv(Device *dev, size_t dbEntries, int alphabetSize, int maxSeqLength, size_t maxSeqs, AlignmentType type = GAPLESS)
+        : dev_(dev), dbEntries_(dbEntries), alphabetSize_(alphabetSize), maxSeqs_(maxSeqs), type_(type), minScoreExcl_(0) {
+        (void) maxSeqLength;
+    }
+
+    // The padded GPU DB of makepaddedseqdb (src/util/makepaddedseqdb.cpp:66-98): numeric codes, +32 = soft-masked,
+    // every entry padded to a multiple of 4 with code 20.  offset[i] / length[i] as ungappedprefilter.cpp:132-136 builds
+    // them.  Masked residues are mapped to X (alphabetSize-1) as runFilterOnCpu does (ungappedprefilter.cpp:402-405).
+    void *loadDb(char *data, size_t *offset, int32_t *length, size_t dbByteSize) {
+        (void) dbByteSize;
+        std::vector<uint8_t> res;
+        std::vector<uint64_t> off(dbEntries_ + 1, 0);
+        for (size_t i = 0; i < dbEntries_; i++) {
+            off[i] = res.size();
+            const unsigned char *s = reinterpret_cast<const unsigned char *>(data) + offset[i];
+            for (int32_t j = 0; j < length[i]; j++) res.push_back(s[j] >= 32 ? (uint8_t) (alphabetSize_ - 1) : (uint8_t) s[j]);
+        }
+        off[dbEntries_] = res.size();
+        lastStatus_ = b200_db_load(dev_->ctx(), res.data(), off.data(), dbEntries_, alphabetSize_);
+        return dev_;
+    }
+    void setDb(void *) {}
+    void prefetch() {}
+    void setMinScore(int minScoreExcl) { minScoreExcl_ = minScoreExcl; }  // minDiagScoreThr, applied on the device
+    int lastStatus() const { return lastStatus_; }
+
+    // pssm: [alphabetSize][sequenceLength] int8 exactly as ungappedprefilter.cpp:195-203 fills it; `bias` is the SSW
+    // profile bias (b200h_ssw_bias) that makes the u8 saturation of the CPU scorer reproducible.
+    Stats scan(const char *sequence, size_t sequenceLength, int8_t *pssm, Result *results, int bias) {
+        (void) sequence;
+        Stats st; st.results = 0; st.numOverflows = 0; st.seconds = 0; st.gcups = 0;
+        b200_query q; q.profile = pssm; q.qlen = (int32_t) sequenceLength; q.bias = bias;
+        hits_.resize(maxSeqs_);
+        uint32_t n = 0;
+        lastStatus_ = b200_ungapped_scan(dev_->ctx(), &q, 1, minScoreExcl_, (uint32_t) maxSeqs_, hits_.data(), &n, NULL);
+        if (lastStatus_ != B200_OK) return st;
+        for (uint32_t i = 0; i < n; i++) results[i] = Result(hits_[i].id, hits_[i].score, 0, 0);
+        st.results = n;
+        return st;
+    }
+
+private:
+    Device *dev_;
+    size_t dbEntries_;
+    int alphabetSize_;
+    size_t maxSeqs_;
+    AlignmentType type_;
+    int minScoreExcl_;
+    int lastStatus_ = B200_OK;
+    std::vector<b200_hit> hits_;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// UngappedAlignment: per-(target, diagonal) scorer used inside the k-mer prefilter.
+// ---------------------------------------------------------------------------------------------------------------
+struct __attribute__((__packed__)) CounterResult {  // src/prefiltering/CacheFriendlyOperations.h:46-51
+    unsigned int id;
+    unsigned short diagonal;
+    unsigned char count;
+};
+
+class UngappedAlignment {
+public:
+    // subMatrix: A*A int16 row-major copy of BaseMatrix::subMatrix; the lookup must already be loaded into `dev`
+    UngappedAlignment(Device *dev, const int16_t *subMatrix, int alphabetSize)
+        : dev_(dev), mat_(subMatrix, subMatrix + (size_t) alphabetSize * alphabetSize), A_(alphabetSize), qlen_(0) {}
+
+    // createProfile(Sequence*, float* biasCorrection)   UngappedAlignment.cpp:388-421
+    int createProfile(const unsigned char *numSequence, int L, const float *biasCorrection) {
+        qlen_ = L;
+        cb_.assign(L, 0);
+        if (biasCorrection != NULL) b200h_round_bias_diag(biasCorrection, L, cb_.data());
+        profile_.resize((size_t) A_ * L);
+        return b200h_build_profile(mat_.data(), A_, numSequence, L, cb_.data(), /*target_major=*/0, profile_.data());
+    }
+
+    // align(CounterResult*, n)   UngappedAlignment.cpp:36-42 -- counts updated in place
+    int align(CounterResult *results, size_t n) { return run(results, n, NULL); }
+
+    // scoreSingelSequenceByCounterResult for a batch (QueryMatcher::getResult re-scores clamped hits, :448-450)
+    int rescore(CounterResult *results, size_t n, int32_t *raw) { return run(results, n, raw); }
+
+private:
+    int run(CounterResult *results, size_t n, int32_t *raw) {
+        ids_.resize(n); diags_.resize(n); counts_.resize(n);
+        for (size_t i = 0; i < n; i++) { ids_[i] = results[i].id; diags_[i] = results[i].diagonal; counts_[i] = results[i].count; }
+        b200_query q; q.profile = profile_.data(); q.qlen = qlen_; q.bias = 0;
+        const int rc = b200_diag_score(dev_->ctx(), &q, ids_.data(), diags_.data(), n, counts_.data(), raw);
+        if (rc == B200_OK) for (size_t i = 0; i < n; i++) results[i].count = counts_[i];
+        return rc;
+    }
+    Device *dev_;
+    std::vector<int16_t> mat_;
+    int A_, qlen_;
+    std::vector<int8_t> cb_, profile_;
+    std::vector<uint32_t> ids_;
+    std::vector<uint16_t> diags_;
+    std::vector<uint8_t> counts_;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// SmithWaterman: ssw_init once per query, then the query's whole prefilter list in one flush.
+// ---------------------------------------------------------------------------------------------------------------
+struct s_align {  // the fields of StripedSmithWaterman.h:59-74 this path produces
+    uint32_t score1;
+    int32_t dbStartPos1, dbEndPos1, qStartPos1, qEndPos1;
+    float qCov, tCov;
+    int word;
+};
+
+class SmithWaterman {
+public:
+    SmithWaterman(Device *dev, const int16_t *subMatrix, const double *pBack, int alphabetSize, bool aaBiasCorrection,
+                  float aaBiasCorrectionScale)
+        : dev_(dev), mat_(subMatrix, subMatrix + (size_t) alphabetSize * alphabetSize), pback_(pBack, pBack + alphabetSize),
+          A_(alphabetSize), biasCorr_(aaBiasCorrection), scale_(aaBiasCorrectionScale), qlen_(0), bias_(0) {}
+
+    // ssw_init(const Sequence* q, const int8_t* mat, const BaseMatrix* m)   StripedSmithWaterman.cpp:1364-1476
+    int ssw_init(const unsigned char *numSequence, int L) {
+        qlen_ = L;
+        cb_.assign(L, 0);
+        if (biasCorr_) {
+            tmp_.resize(L);
+            b200h_comp_bias(mat_.data(), pback_.data(), A_, numSequence, L, scale_, tmp_.data());
+            b200h_round_bias_ssw(tmp_.data(), L, cb_.data());
+        }
+        bias_ = b200h_ssw_bias(mat_.data(), A_, cb_.data(), L, biasCorr_ ? 1 : 0);
+        profile_.resize((size_t) A_ * L);
+        targets_.clear();
+        return b200h_build_profile(mat_.data(), A_, numSequence, L, cb_.data(), /*target_major=*/1, profile_.data());
+    }
+
+    void addTarget(uint32_t dbId) { targets_.push_back(dbId); }
+    size_t pending() const { return targets_.size(); }
+
+    static float computeCov(unsigned int startPos, unsigned int endPos, unsigned int len) {  // StripedSmithWaterman.cpp:1762
+        return (std::min(len, std::max(startPos, endPos)) - std::min(startPos, endPos) + 1) / (float) len;
+    }
+
+    // Resolves every pending target the way ssw_align_private does (StripedSmithWaterman.cpp:831-890), alignment modes
+    // 0/1/2 up to start positions:
+    //   1. score of all targets (packed kernel)
+    //   2. gateScore(score1, userData) -> false: the hit is dropped before positions are computed (E-value gate;
+    //      such hits fail Alignment::checkCriteria anyway, Alignment.cpp:389)
+    //   3. end positions of the survivors; gateCov(qCov, tCov, userData) as hasLowerCoverage does with start 0
+    //   4. start positions of the remaining ones (alignmentMode >= 1)
+    // dbLen[i] is needed for the coverage values only.  out[i].dbEndPos1 == -1 marks "no residue aligned" or "gated out".
+    typedef bool (*GateScore)(uint32_t score1, void *userData);
+    typedef bool (*GateCov)(float qCov, float tCov, void *userData);
+    int flush(const int32_t *dbLen, uint8_t gapOpen, uint8_t gapExtend, uint8_t alignmentMode, GateScore gateScore,
+              GateCov gateCov, void *userData, std::vector<s_align> &out) {
+        const size_t n = targets_.size();
+        out.resize(n);
+        if (n == 0) return B200_OK;
+        b200_query q; q.profile = profile_.data(); q.qlen = qlen_; q.bias = bias_;
+        std::vector<b200_pair> pairs(n);
+        for (size_t i = 0; i < n; i++) { pairs[i].query = 0; pairs[i].target = targets_[i]; }
+        std::vector<int32_t> score(n);
+        int rc = b200_sw_score(dev_->ctx(), &q, 1, pairs.data(), n, gapOpen, gapExtend, score.data());
+        if (rc != B200_OK) return rc;
+        std::vector<b200_pair> sub;
+        std::vector<size_t> idx;
+        for (size_t i = 0; i < n; i++) {
+            s_align &r = out[i];
+            r.score1 = (uint32_t) score[i]; r.dbStartPos1 = -1; r.qStartPos1 = -1; r.dbEndPos1 = -1; r.qEndPos1 = qlen_ - 1;
+            r.qCov = 0; r.tCov = 0; r.word = (score[i] + bias_ >= 255) ? 1 : 0;
+            if (score[i] > 0 && (gateScore == NULL || gateScore(r.score1, userData))) { sub.push_back(pairs[i]); idx.push_back(i); }
+        }
+        if (sub.empty()) { targets_.clear(); return B200_OK; }
+        std::vector<b200_sw_end> ends(sub.size());
+        rc = b200_sw_score_endpos(dev_->ctx(), &q, 1, sub.data(), sub.size(), gapOpen, gapExtend, ends.data());
+        if (rc != B200_OK) return rc;
+        std::vector<b200_pair> sub2;
+        std::vector<b200_sw_end> ends2;
+        std::vector<size_t> idx2;
+        for (size_t k = 0; k < sub.size(); k++) {
+            s_align &r = out[idx[k]];
+            r.qEndPos1 = ends[k].qend; r.dbEndPos1 = ends[k].dbend; r.word = ends[k].word;
+            if (ends[k].dbend == -1) continue;
+            r.qCov = computeCov(0, r.qEndPos1, qlen_);
+            r.tCov = computeCov(0, r.dbEndPos1, dbLen[idx[k]]);
+            const bool covOk = gateCov == NULL || gateCov(r.qCov, r.tCov, userData);
+            if (alignmentMode == 0 || !covOk) continue;
+            sub2.push_back(sub[k]); ends2.push_back(ends[k]); idx2.push_back(idx[k]);
+        }
+        if (!sub2.empty()) {
+            std::vector<b200_sw_aln> aln(sub2.size());
+            rc = b200_sw_startpos(dev_->ctx(), &q, 1, sub2.data(), sub2.size(), gapOpen, gapExtend, ends2.data(), aln.data());
+            if (rc != B200_OK) return rc;
+            for (size_t k = 0; k < sub2.size(); k++) {
+                s_align &r = out[idx2[k]];
+                r.qStartPos1 = aln[k].qstart; r.dbStartPos1 = aln[k].dbstart;
+                r.qCov = computeCov(r.qStartPos1, r.qEndPos1, qlen_);
+                r.tCov = computeCov(r.dbStartPos1, r.dbEndPos1, dbLen[idx2[k]]);
+            }
+        }
+        targets_.clear();
+        return B200_OK;
+    }
+
+    int bias() const { return bias_; }
+    const int8_t *compositionBias() const { return cb_.data(); }
+
+private:
+    Device *dev_;
+    std::vector<int16_t> mat_;
+    std::vector<double> pback_;
+    int A_;
+    bool biasCorr_;
+    float scale_;
+    int qlen_, bias_;
+    std::vector<float> tmp_;
+    std::vector<int8_t> cb_, profile_;
+    std::vector<uint32_t> targets_;
+};
+
+}  // namespace b200
+#endif  // B200_MMSEQS_HPP

@@ -582,58 +582,20 @@ __device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t se
 }
 
 template <int K, bool SMEM>
-__global__ void __launch_bounds__(SW_WARPS * 32)
-sw16_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd, const WorkItem *__restrict__ items,
-            const PairDesc *__restrict__ pairs, const uint8_t *__restrict__ db, const uint64_t *__restrict__ off,
-            const int32_t *__restrict__ len, int A, int go, int ge, uint2 *__restrict__ bnd, int bnd_stride,
-            int smem_profile, unsigned n_items, unsigned *__restrict__ item_counter, int32_t *__restrict__ out) {
+__device__ __forceinline__ void sw16_item(const int8_t *prof_base, const QueryDesc &q, const WorkItem &item,
+                                          const PairDesc *__restrict__ pairs, const uint8_t *__restrict__ db,
+                                          const uint64_t *__restrict__ off, const int32_t *__restrict__ len, int A, int go,
+                                          int ge, uint2 *bnd0, uint2 *bnd1, unsigned *next_pair_ptr, int32_t *__restrict__ out) {
     static_assert(K % 4 == 0 && K <= 16, "K in {4,8,12,16}");
     constexpr int W = K / 4;
     constexpr int TILE = 32 * K;
-    extern __shared__ __align__(16) int8_t smem_prof[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ unsigned next_pair;
-    __shared__ unsigned cur_item;
-
     const int lane = threadIdx.x & 31;
-    const int warp_global = blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
-    uint2 *bnd0 = bnd + (size_t) warp_global * 2 * bnd_stride;
-    uint2 *bnd1 = bnd0 + bnd_stride;
+    const int Lp = q.Lp;
     const uint32_t neg_ge2 = pack16(-ge, -ge), neg_go2 = pack16(-go, -go);
     const uint32_t padres = (uint32_t) A | ((uint32_t) A << 8);
-    unsigned phase = 0;
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-
-  while (true) {
-    __syncthreads();
-    if (threadIdx.x == 0) cur_item = atomicAdd(item_counter, 1u);
-    __syncthreads();
-    const unsigned item_idx = cur_item;
-    if (item_idx >= n_items) break;
-    const WorkItem item = items[item_idx];
-    const QueryDesc q = qd[item.query];
-    const int8_t *gprof = padded + q.pad_off;
-    const int Lp = q.Lp;
-    if (threadIdx.x == 0) next_pair = item.p0;
-    if (SMEM) {
-        const unsigned bytes = (unsigned) ((A + 1) * Lp);
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(&bar, bytes);
-            for (unsigned o = 0; o < bytes; o += 32768u) bulk_g2s(smem_prof + o, gprof + o, min(32768u, bytes - o), &bar);
-        }
-        __syncthreads();
-        mbar_wait(&bar, phase);
-        phase ^= 1u;
-    } else {
-        __syncthreads();
-    }
-
     while (true) {
         unsigned p = 0;
-        if (lane == 0) p = atomicAdd(&next_pair, 2u);
+        if (lane == 0) p = atomicAdd(next_pair_ptr, 2u);
         p = __shfl_sync(0xffffffffu, p, 0);
         if (p >= item.p1) break;
         const bool has_b = p + 1 < item.p1;
@@ -644,7 +606,7 @@ sw16_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd,
         const int tiles = (q.qlen + TILE - 1) / TILE;
         uint32_t best = 0;
         for (int tile = 0; tile < tiles; tile++) {
-            const int8_t *pptr = (SMEM ? (const int8_t *) smem_prof : gprof) + tile * TILE + lane * K;
+            const int8_t *pptr = prof_base + tile * TILE + lane * K;
             uint2 *bnd_rd = (tile & 1) ? bnd0 : bnd1;
             uint2 *bnd_wr = (tile & 1) ? bnd1 : bnd0;
             const bool write_bnd = tile + 1 < tiles;
@@ -729,7 +691,58 @@ sw16_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd,
             if (has_b) out[p + 1] = (int) (best >> 16);
         }
     }
-  }
+}
+
+// One launch covers every query length: items carry the rows-per-lane flavour (4/8/12/16) chosen for their query.
+template <bool SMEM>
+__global__ void __launch_bounds__(SW_WARPS * 32, 6)
+sw16_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd, const WorkItem *__restrict__ items,
+            const PairDesc *__restrict__ pairs, const uint8_t *__restrict__ db, const uint64_t *__restrict__ off,
+            const int32_t *__restrict__ len, int A, int go, int ge, uint2 *__restrict__ bnd, int bnd_stride,
+            unsigned n_items, unsigned *__restrict__ item_counter, int32_t *__restrict__ out) {
+    extern __shared__ __align__(16) int8_t smem_prof[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ unsigned next_pair;
+    __shared__ unsigned cur_item;
+
+    const int warp_global = blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
+    uint2 *bnd0 = bnd + (size_t) warp_global * 2 * bnd_stride;
+    uint2 *bnd1 = bnd0 + bnd_stride;
+    unsigned phase = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) cur_item = atomicAdd(item_counter, 1u);
+        __syncthreads();
+        const unsigned item_idx = cur_item;
+        if (item_idx >= n_items) break;
+        const WorkItem item = items[item_idx];
+        const QueryDesc q = qd[item.query];
+        const int8_t *gprof = padded + q.pad_off;
+        if (threadIdx.x == 0) next_pair = item.p0;
+        if (SMEM) {
+            const unsigned bytes = (unsigned) ((A + 1) * q.Lp);
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&bar, bytes);
+                for (unsigned o = 0; o < bytes; o += 32768u) bulk_g2s(smem_prof + o, gprof + o, min(32768u, bytes - o), &bar);
+            }
+            __syncthreads();
+            mbar_wait(&bar, phase);
+            phase ^= 1u;
+        } else {
+            __syncthreads();
+        }
+        const int8_t *pb = SMEM ? (const int8_t *) smem_prof : gprof;
+        switch (item.pad_) {
+            case 4: sw16_item<4, SMEM>(pb, q, item, pairs, db, off, len, A, go, ge, bnd0, bnd1, &next_pair, out); break;
+            case 8: sw16_item<8, SMEM>(pb, q, item, pairs, db, off, len, A, go, ge, bnd0, bnd1, &next_pair, out); break;
+            case 12: sw16_item<12, SMEM>(pb, q, item, pairs, db, off, len, A, go, ge, bnd0, bnd1, &next_pair, out); break;
+            default: sw16_item<16, SMEM>(pb, q, item, pairs, db, off, len, A, go, ge, bnd0, bnd1, &next_pair, out); break;
+        }
+    }
 }
 
 // ================================================================================================
@@ -1152,7 +1165,24 @@ int b200_diag_score(b200_ctx *ctx, const b200_query *q, const uint32_t *ids, con
 // ---- A3-A5 ------------------------------------------------------------------------------------------
 namespace {
 
-constexpr uint32_t kPairsPerItem = 32;
+constexpr uint32_t kPairsPerItem = 8;
+
+// rows per lane of the packed kernel for a query length: least padded rows, ties to the larger tile
+int sw16_k_for(int qlen) {
+    int bestK = 16;
+    long best_rows = -1;
+    const int ks[4] = {4, 8, 12, 16};
+    for (int i = 0; i < 4; i++) {
+        const long tile = 32L * ks[i];
+        const long rows = (qlen + tile - 1) / tile * tile;
+        const long tiles = rows / tile;
+        const long cost = rows + 40 * tiles;  // a tile restart costs about a 32-step pipeline fill
+        if (best_rows < 0 || cost <= best_rows) { best_rows = cost; bestK = ks[i]; }
+    }
+    return bestK;
+}
+
+
 
 struct SwPlan {
     std::vector<uint32_t> perm;  // sorted position -> caller index
@@ -1179,7 +1209,7 @@ void plan_pairs(const b200_ctx *ctx, const b200_query *queries, const b200_pair 
         const uint32_t qy = pairs[plan.perm[s]].query;
         while (e < m && pairs[plan.perm[e]].query == qy) e++;
         for (uint32_t p = s; p < e; p += kPairsPerItem) {
-            WorkItem it; it.query = qy; it.p0 = p; it.p1 = std::min(e, p + kPairsPerItem); it.pad_ = 0;
+            WorkItem it; it.query = qy; it.p0 = p; it.p1 = std::min(e, p + kPairsPerItem); it.pad_ = (uint32_t) sw16_k_for(qlens[qy]);
             plan.items.push_back(it);
         }
         s = e;
@@ -1451,60 +1481,30 @@ int b200_sw_job_create(b200_ctx *ctx, const b200_query *queries, int nq, const b
 // ---- score-only batch (packed int16x2 fast path + int32 fallback) ---------------------------------------------
 namespace {
 
-// rows per lane of the packed kernel for a query length: least padded rows, ties to the larger tile
-int sw16_k_for(int qlen) {
-    int bestK = 16;
-    long best_rows = -1;
-    const int ks[4] = {4, 8, 12, 16};
-    for (int i = 0; i < 4; i++) {
-        const long tile = 32L * ks[i];
-        const long rows = (qlen + tile - 1) / tile * tile;
-        const long tiles = rows / tile;
-        const long cost = rows + 40 * tiles;  // a tile restart costs about a 32-step pipeline fill
-        if (best_rows < 0 || cost <= best_rows) { best_rows = cost; bestK = ks[i]; }
-    }
-    return bestK;
-}
-
-template <int K>
-cudaError_t launch_sw16_k(b200_ctx *ctx, const QueryDesc *d_qd, const int8_t *d_pad, size_t smem, int smem_profile,
-                          const WorkItem *d_items, uint32_t n_items, const PairDesc *d_pairs, int go, int ge, uint2 *d_bnd,
-                          int bnd_stride, int32_t *d_out) {
-    int per_sm = 0;
-    if (smem_profile) {
-        cudaError_t e = cudaFuncSetAttribute(sw16_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-        if (e != cudaSuccess) return e;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw16_kernel<K, true>, SW_WARPS * 32, smem) != cudaSuccess) per_sm = 1;
-    } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw16_kernel<K, false>, SW_WARPS * 32, 0) != cudaSuccess) per_sm = 1;
-    per_sm = std::max(1, per_sm);
-    const unsigned grid = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) ctx->sm_count * per_sm, n_items));
-    if (smem_profile)
-        sw16_kernel<K, true><<<grid, SW_WARPS * 32, smem, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
-                                                                        ctx->d_len, ctx->alphabet, go, ge, d_bnd, bnd_stride,
-                                                                        smem_profile, n_items, ctx->counter.as<unsigned>(), d_out);
-    else
-        sw16_kernel<K, false><<<grid, SW_WARPS * 32, 0, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
-                                                                      ctx->d_len, ctx->alphabet, go, ge, d_bnd, bnd_stride,
-                                                                      smem_profile, n_items, ctx->counter.as<unsigned>(), d_out);
-    return cudaGetLastError();
-}
-
-int launch_sw16(b200_ctx *ctx, int K, const QueryDesc *d_qd, const int8_t *d_pad, int max_Lp, const WorkItem *d_items,
-                uint32_t n_items, const PairDesc *d_pairs, int go, int ge, uint2 *d_bnd, int bnd_stride, int32_t *d_out) {
+int launch_sw16(b200_ctx *ctx, const QueryDesc *d_qd, const int8_t *d_pad, int max_Lp, const WorkItem *d_items, uint32_t n_items,
+                const PairDesc *d_pairs, int go, int ge, uint2 *d_bnd, int bnd_stride, int32_t *d_out) {
     size_t smem = (size_t) (ctx->alphabet + 1) * max_Lp;
     int smem_profile = 1;
     if (smem > (size_t) ctx->max_smem_optin - 1024) { smem = 0; smem_profile = 0; }
     CU_TRY(ctx, ctx->counter.reserve(sizeof(unsigned)));
     CU_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(unsigned), ctx->stream));
-    cudaError_t e;
-    switch (K) {
-        case 4: e = launch_sw16_k<4>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out); break;
-        case 8: e = launch_sw16_k<8>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out); break;
-        case 12: e = launch_sw16_k<12>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out); break;
-        default: e = launch_sw16_k<16>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out); break;
-    }
+    int per_sm = 0;
+    if (smem_profile) {
+        CU_TRY(ctx, cudaFuncSetAttribute(sw16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw16_kernel<true>, SW_WARPS * 32, smem) != cudaSuccess) per_sm = 1;
+    } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw16_kernel<false>, SW_WARPS * 32, 0) != cudaSuccess) per_sm = 1;
+    per_sm = std::max(1, per_sm);
+    const unsigned grid = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) ctx->sm_count * per_sm, n_items));
+    if (smem_profile)
+        sw16_kernel<true><<<grid, SW_WARPS * 32, smem, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off, ctx->d_len,
+                                                                     ctx->alphabet, go, ge, d_bnd, bnd_stride, n_items,
+                                                                     ctx->counter.as<unsigned>(), d_out);
+    else
+        sw16_kernel<false><<<grid, SW_WARPS * 32, 0, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off, ctx->d_len,
+                                                                   ctx->alphabet, go, ge, d_bnd, bnd_stride, n_items,
+                                                                   ctx->counter.as<unsigned>(), d_out);
     ctx->launches++;
-    CU_TRY(ctx, e);
+    CU_TRY(ctx, cudaGetLastError());
     return B200_OK;
 }
 
@@ -1524,29 +1524,28 @@ int b200_sw_score_job_create(b200_ctx *ctx, const b200_query *queries, int nq, c
     if (rc != B200_OK) return rc;
     const int A = ctx->alphabet;
     // int16 safety: a local alignment cannot score more than min(qlen,tlen) * (largest profile entry)
-    std::vector<int> smax(nq, 1), kq(nq, 16);
+    std::vector<int> smax(nq, 1);
     for (int i = 0; i < nq; i++) {
         int m = 1;
         const int8_t *pr = queries[i].profile;
         for (size_t k = 0; k < (size_t) A * queries[i].qlen; k++) m = std::max(m, (int) pr[k]);
         smax[i] = m;
-        kq[i] = sw16_k_for(queries[i].qlen);
     }
     b200_job *job = new b200_job();
     job->ctx = ctx; job->kind = 3; job->go = go; job->ge = ge; job->n_pairs = n; job->nq = nq;
-    const int klass[5] = {4, 8, 12, 16, 0};
+    const int klass[2] = {1, 0};  // 1: packed int16x2 kernel (any rows-per-lane flavour), 0: int32 fallback
     std::vector<uint8_t> mask(n);
     int max_cols = 1;
     bool multi = false;
     uint32_t max_items = 1;
     cudaError_t e = cudaSuccess;
-    for (int c = 0; c < 5 && e == cudaSuccess; c++) {
+    for (int c = 0; c < 2 && e == cudaSuccess; c++) {
         bool any = false;
         for (uint64_t i = 0; i < n; i++) {
             const int qi = (int) pairs[i].query;
             const int tl = ctx->h_len[pairs[i].target];
             const bool packed_ok = go >= ge && (int64_t) std::min(queries[qi].qlen, tl) * smax[qi] < 32000;
-            const int k = packed_ok ? kq[qi] : 0;
+            const int k = packed_ok ? 1 : 0;
             mask[i] = (k == klass[c]) ? 1 : 0;
             any |= mask[i] != 0;
             if (c == 0) job->cells += (uint64_t) queries[qi].qlen * (uint64_t) tl;
@@ -1562,13 +1561,12 @@ int b200_sw_score_job_create(b200_ctx *ctx, const b200_query *queries, int nq, c
         pt->n_items = (uint32_t) plan.items.size();
         max_items = std::max(max_items, pt->n_items);
         std::vector<PairDesc> h_pd(pt->n_pairs);
-        const int tile = klass[c] ? 32 * klass[c] : SW_TILE;
         for (uint32_t sidx = 0; sidx < pt->n_pairs; sidx++) {
             const uint32_t i = plan.perm[sidx];
             h_pd[sidx].target = pairs[i].target; h_pd[sidx].qend = h_pd[sidx].dbend = h_pd[sidx].score = 0;
             max_cols = std::max(max_cols, ctx->h_len[pairs[i].target]);
             pt->max_Lp = std::max(pt->max_Lp, h_qd[pairs[i].query].Lp);
-            if (queries[pairs[i].query].qlen > tile) multi = true;
+            if (queries[pairs[i].query].qlen > (klass[c] ? 32 * sw16_k_for(queries[pairs[i].query].qlen) : SW_TILE)) multi = true;
         }
         e = pt->pairs.reserve(sizeof(PairDesc) * pt->n_pairs);
         if (e == cudaSuccess) e = pt->items.reserve(sizeof(WorkItem) * pt->n_items);
@@ -1599,7 +1597,7 @@ static int sw_score_job_run_locked(b200_job *job) {
     for (b200_job::Part *pt : job->parts) {
         int rc;
         if (pt->K > 0)
-            rc = launch_sw16(ctx, pt->K, job->qdesc.as<QueryDesc>(), job->pad.as<int8_t>(), pt->max_Lp, pt->items.as<WorkItem>(),
+            rc = launch_sw16(ctx, job->qdesc.as<QueryDesc>(), job->pad.as<int8_t>(), pt->max_Lp, pt->items.as<WorkItem>(),
                              pt->n_items, pt->pairs.as<PairDesc>(), job->go, job->ge, job->bnd.as<uint2>(), job->bnd_stride,
                              pt->out.as<int32_t>());
         else

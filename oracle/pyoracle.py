@@ -153,6 +153,17 @@ class Ref:
                                      go, ge, _p(out), nthreads)
         return out
 
+    def sw_score_endpos_multi(self, queries, comp_bias, tdata, toff, pairs, go=11, ge=1, nthreads=8):
+        """pairs: uint32 [n][2] grouped by query; one OpenMP region over queries (the shape of Alignment::run)"""
+        qd, qo = pack_targets(queries)
+        pq = np.ascontiguousarray(pairs[:, 0], np.uint32)
+        pt = np.ascontiguousarray(pairs[:, 1], np.uint32)
+        out = np.zeros((len(pq), 4), np.int32)
+        to = np.ascontiguousarray(toff, np.int64)
+        self.lib.ref_sw_score_endpos_multi(_p(qd), _p(qo), ctypes.c_int64(len(queries)), 1 if comp_bias else 0, _p(tdata), _p(to),
+                                           _p(pq), _p(pt), ctypes.c_int64(len(pq)), go, ge, _p(out), nthreads)
+        return out
+
     def ssw_align(self, q, comp_bias, tdata, toff, go=11, ge=1, mode=1, eval_thr=1e300, cov_mode=0, cov_thr=0.0,
                   db_residues=10**9, want_bt=False, nthreads=8):
         q = np.ascontiguousarray(q, np.uint8)
