@@ -177,12 +177,13 @@ def cpu_reference_sw(queries, td, to, pairs, budget_s, threads):
     cells_pair = np.array([len(queries[a]) * int(to64[b + 1] - to64[b]) for a, b in pairs], np.float64)
     if Ref.available():
         ref = Ref()
-        probe = pairs[pairs[:, 0] < 8]
+        per_q = max(1, len(pairs) // len(queries))
+        probe = pairs[pairs[:, 0] < min(len(queries), 2 * threads)]
         t0 = time.perf_counter()
         ref.sw_score_endpos_multi(queries, True, td, to64, probe, nthreads=threads)
-        dt0 = max(time.perf_counter() - t0, 1e-3)
-        rate = cells_pair[:len(probe)].sum() / dt0
-        nq = int(min(len(queries), max(threads, np.searchsorted(np.cumsum(cells_pair), rate * budget_s) // max(1, len(pairs) // len(queries)))))
+        rate = cells_pair[:len(probe)].sum() / max(time.perf_counter() - t0, 1e-3)
+        want_pairs = int(np.searchsorted(np.cumsum(cells_pair), rate * budget_s))
+        nq = int(min(len(queries), max(2 * threads, want_pairs // per_q)))
         sub = pairs[pairs[:, 0] < nq]
         t0 = time.perf_counter()
         ref.sw_score_endpos_multi(queries, True, td, to64, sub, nthreads=threads)
@@ -257,7 +258,7 @@ def main():
     ap.add_argument("--queries-per-step", type=int, default=16)
     ap.add_argument("--max-hits", type=int, default=300)
     ap.add_argument("--no-secondary", action="store_true")
-    ap.add_argument("--sw-queries", type=int, default=192)
+    ap.add_argument("--sw-queries", type=int, default=512)
     ap.add_argument("--sw-targets", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

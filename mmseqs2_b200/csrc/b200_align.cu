@@ -35,19 +35,53 @@
 
 static inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
 
+// Device scratch.  cudaMalloc/cudaFree cost hundreds of microseconds each and synchronise the device, so released
+// buffers go to a small per-process free list (best fit, bounded) instead of back to the driver; one-shot calls such as
+// b200_sw_score then run without touching the allocator after warm-up.
+struct DevPool {
+    struct Slot { void *p; size_t cap; int dev; };
+    std::mutex mu;
+    std::vector<Slot> free_list;
+    size_t held = 0;
+    static DevPool &get() { static DevPool pool; return pool; }
+    void *take(size_t n, int dev, size_t *cap_out) {
+        std::lock_guard<std::mutex> lk(mu);
+        int best = -1;
+        for (size_t i = 0; i < free_list.size(); i++)
+            if (free_list[i].dev == dev && free_list[i].cap >= n && free_list[i].cap <= 4 * n + (1u << 20) &&
+                (best < 0 || free_list[i].cap < free_list[best].cap)) best = (int) i;
+        if (best < 0) return nullptr;
+        void *p = free_list[best].p;
+        *cap_out = free_list[best].cap;
+        held -= free_list[best].cap;
+        free_list.erase(free_list.begin() + best);
+        return p;
+    }
+    void give(void *p, size_t cap, int dev) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (free_list.size() >= 64 || held + cap > ((size_t) 8 << 30)) { cudaFree(p); return; }
+        Slot s = {p, cap, dev};
+        free_list.push_back(s);
+        held += cap;
+    }
+};
+
 struct DevBuf {  // grow-only device scratch
     void *p = nullptr;
     size_t cap = 0;
+    int dev = 0;
     cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = n + n / 4 + 256;
+        release();
+        cudaGetDevice(&dev);
+        const size_t want = n + n / 4 + 256;
+        p = DevPool::get().take(want, dev, &cap);
+        if (p) return cudaSuccess;
         cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
+        if (e == cudaSuccess) cap = want; else p = nullptr;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) DevPool::get().give(p, cap, dev); p = nullptr; cap = 0; }
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
@@ -154,7 +188,8 @@ template <int G, int K>
 __global__ void __launch_bounds__(256)
 ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict__ qd, const uint8_t *__restrict__ db,
                      const uint64_t *__restrict__ off, const int32_t *__restrict__ len,
-                     const uint32_t *__restrict__ order, uint32_t n_seq, int A, uint8_t *__restrict__ out) {
+                     const uint32_t *__restrict__ order, uint32_t n_seq, int A, uint8_t *__restrict__ out, uint32_t n_queries,
+                     uint32_t units_per_query, uint32_t unit_targets, unsigned *__restrict__ unit_counter) {
     static_assert(K % 4 == 0, "K must be a multiple of 4");
     constexpr int C = K / 4;
     constexpr int ROW_U4 = C * G;  // uint4 per residue row
@@ -162,16 +197,36 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
     uint4 *P = smem_u4;
     uint4 *Pp = smem_u4 + (size_t) (A + 1) * ROW_U4;
 
-    const QueryDesc q = qd[blockIdx.y];
-    const int8_t *prof = raw + q.raw_off;
-    const int qlen = q.qlen;
-    {
+    __shared__ unsigned cur_unit;
+    const int lane = threadIdx.x & 31;
+    const int g = lane % G;
+    constexpr int GROUPS_PER_WARP = 32 / G;
+    const uint32_t warps_per_cta = blockDim.x >> 5;
+    const uint32_t warp_in_cta = threadIdx.x >> 5;
+    const uint32_t padword = (uint32_t) A * 0x01010101u;
+    int cur_q = -1;
+    uint32_t cst = 0;
+
+  // persistent CTA: work units = (query, chunk of the length-sorted target order), handed out query-major / longest
+  // targets first by a global counter; the profile tables are rebuilt only when the query changes
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) cur_unit = atomicAdd(unit_counter, 1u);
+    __syncthreads();
+    const uint32_t unit = cur_unit;
+    if (unit >= n_queries * units_per_query) break;
+    const int qi = (int) (unit / units_per_query);
+    const uint32_t chunk = unit % units_per_query;
+    if (qi != cur_q) {
+        const QueryDesc q = qd[qi];
+        const int8_t *prof = raw + q.raw_off;
+        const int qlen = q.qlen;
         uint32_t *Pw = reinterpret_cast<uint32_t *>(P);
         uint32_t *Ppw = reinterpret_cast<uint32_t *>(Pp);
         const int words = G * K;
         for (int idx = threadIdx.x; idx < (A + 1) * words; idx += blockDim.x) {
             const int a = idx / words, w = idx % words;
-            const int g = w / K, r = w % K, c = r >> 2, e = r & 3;
+            const int gg = w / K, r = w % K, c = r >> 2, e = r & 3;
             int s0 = 0, s1 = 0, sm1 = 0;  // rows 2w, 2w+1, 2w-1
             if (a < A) {
                 const int8_t *pa = prof + (size_t) a * qlen;
@@ -179,27 +234,22 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
                 if (2 * w + 1 < qlen) s1 = pa[2 * w + 1];
                 if (2 * w - 1 >= 0 && 2 * w - 1 < qlen) sm1 = pa[2 * w - 1];
             }
-            const int dst = (a * ROW_U4 + c * G + g) * 4 + e;
+            const int dst = (a * ROW_U4 + c * G + gg) * 4 + e;
             Pw[dst] = pack16(s0, s1);
             Ppw[dst] = pack16(sm1, s0);
         }
+        cst = (uint32_t) (255 - q.bias) * 0x00010001u;
+        cur_q = qi;
+        __syncthreads();
     }
-    __syncthreads();
+    uint8_t *outq = out + (size_t) qi * n_seq;
+    const uint32_t unit_end = min(n_seq, (chunk + 1) * unit_targets);
 
-    const int lane = threadIdx.x & 31;
-    const int g = lane % G;
-    constexpr int GROUPS_PER_WARP = 32 / G;
-    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
-    const uint32_t warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const uint32_t cst = (uint32_t) (255 - q.bias) * 0x00010001u;
-    const uint32_t padword = (uint32_t) A * 0x01010101u;
-    uint8_t *outq = out + (size_t) blockIdx.y * n_seq;
-
-    for (uint32_t base = warp_id * GROUPS_PER_WARP; base < n_seq; base += warps_total * GROUPS_PER_WARP) {
+    for (uint32_t base = chunk * unit_targets + warp_in_cta * GROUPS_PER_WARP; base < unit_end; base += warps_per_cta * GROUPS_PER_WARP) {
         const uint32_t it = base + lane / G;
         uint32_t tid = 0;
         int tl = 0;
-        if (it < n_seq) { tid = order[it]; tl = len[tid]; }
+        if (it < unit_end) { tid = order[it]; tl = len[tid]; }
         const uint4 *tp = reinterpret_cast<const uint4 *>(db + off[tid]);
         int maxl = tl;
 #pragma unroll
@@ -254,8 +304,9 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
         int m = max((int) (best & 0xffffu), (int) (best >> 16));
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (g == 0 && it < n_seq) outq[tid] = (uint8_t) m;
+        if (g == 0 && it < unit_end) outq[tid] = (uint8_t) m;
     }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -764,13 +815,20 @@ cudaError_t launch_scan_cfg(b200_ctx *ctx, const int8_t *raw, const QueryDesc *q
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ungapped_scan_kernel<G, K>, 256, smem);
     if (e != cudaSuccess) return e;
     per_sm = std::max(per_sm, 1);
-    const uint64_t groups_per_cta = 256 / G;
-    uint64_t ctas = (uint64_t) ctx->sm_count * per_sm;
-    ctas = std::max<uint64_t>(1, std::min<uint64_t>(ctas, (ctx->n_seq + groups_per_cta - 1) / groups_per_cta));
-    if (nq > 1) ctas = std::max<uint64_t>(1, (ctas + nq - 1) / nq);
-    dim3 grid((unsigned) ctas, (unsigned) nq);
-    ungapped_scan_kernel<G, K><<<grid, 256, smem, ctx->stream>>>(raw, qd, ctx->d_res, ctx->d_off, ctx->d_len, ctx->d_order,
-                                                               (uint32_t) ctx->n_seq, ctx->alphabet, dense);
+    const uint64_t resident = (uint64_t) ctx->sm_count * per_sm;
+    const uint32_t groups_per_cta = 256 / G;
+    // ~16 work units per resident CTA over the whole launch, each a multiple of one CTA-wide pass over the sorted targets
+    uint64_t unit_targets = ((uint64_t) ctx->n_seq * nq + resident * 16 - 1) / (resident * 16);
+    unit_targets = std::max<uint64_t>(groups_per_cta, (unit_targets + groups_per_cta - 1) / groups_per_cta * groups_per_cta);
+    const uint32_t units_per_query = (uint32_t) ((ctx->n_seq + unit_targets - 1) / unit_targets);
+    const uint64_t ctas = std::max<uint64_t>(1, std::min<uint64_t>(resident, (uint64_t) units_per_query * nq));
+    e = ctx->counter.reserve(sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->counter.p, 0, sizeof(unsigned), ctx->stream);
+    if (e != cudaSuccess) return e;
+    ungapped_scan_kernel<G, K><<<(unsigned) ctas, 256, smem, ctx->stream>>>(raw, qd, ctx->d_res, ctx->d_off, ctx->d_len, ctx->d_order,
+                                                                           (uint32_t) ctx->n_seq, ctx->alphabet, dense, (uint32_t) nq,
+                                                                           units_per_query, (uint32_t) unit_targets,
+                                                                           ctx->counter.as<unsigned>());
     ctx->launches++;
     return cudaGetLastError();
 }
