@@ -632,18 +632,111 @@ __device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t se
     return d;
 }
 
-template <int K, bool SMEM>
+// One query tile (32*K rows starting at row `row_base`) against the two targets of a warp task, all columns.
+// FIRST: tile 0 (no boundary row to read).  Returns the running packed maximum.
+template <int K, bool FIRST>
+__device__ __forceinline__ uint32_t sw16_tile(const int8_t *pptr, int Lp, const uint8_t *pa_t, const uint8_t *pb_t, int tla,
+                                              int tlb, int ncols, int A, uint32_t neg_ge2, uint32_t neg_go2,
+                                              const uint2 *bnd_rd, uint2 *bnd_wr, bool write_bnd, uint32_t best) {
+    static_assert(K % 4 == 0 && K <= 16, "K in {4,8,12,16}");
+    constexpr int W = K / 4;
+    const int lane = threadIdx.x & 31;
+    const uint32_t padres = (uint32_t) A | ((uint32_t) A << 8);
+    // State per row: H (previous column) and Eh = E + go.  F travels down the column as Fh = F + go.
+    // With go >= ge (host-checked) the recurrences become, per cell,
+    //   Eh' = max(Eh - ge, Hleft)            T = max(Hdiag + s, Eh' - go, 0)
+    //   H   = max(T, Fh - go)                Fh' = max(Fh - ge, T)
+    // all in place: a descending pass (E, T) then an ascending pass (F chain, one dependent op per row).
+    // Lanes that have not reached column 0 yet, or are past the last column, see the pad residue (profile -128):
+    // their cells stay 0 / stay below every real cell, so no per-step range predicate is needed.
+    uint32_t H[K], Eh[K];
+#pragma unroll
+    for (int j = 0; j < K; j++) { H[j] = 0; Eh[j] = 0; }
+    uint32_t hlast = 0, fout = 0, hdiag_in = 0;
+    uint32_t res = padres, tchunk = padres;
+    uint2 bchunk = make_uint2(0, 0);
+    const int nsteps = ncols + 31;
+    for (int step = 0; step < nsteps; step++) {
+        if ((step & 31) == 0) {
+            const int c = step + lane;
+            const uint32_t ra = (c < tla) ? (uint32_t) pa_t[c] : (uint32_t) A;
+            const uint32_t rb = (c < tlb) ? (uint32_t) pb_t[c] : (uint32_t) A;
+            tchunk = ra | (rb << 8);
+            if (!FIRST) bchunk = (c < ncols) ? bnd_rd[c] : make_uint2(0, 0);
+        }
+        const uint32_t r0 = __shfl_sync(0xffffffffu, tchunk, step & 31);
+        res = __shfl_up_sync(0xffffffffu, res, 1);
+        uint32_t hin = __shfl_up_sync(0xffffffffu, hlast, 1);
+        uint32_t fin = __shfl_up_sync(0xffffffffu, fout, 1);
+        if (!FIRST) {
+            const uint32_t bh = __shfl_sync(0xffffffffu, bchunk.x, step & 31);
+            const uint32_t bf = __shfl_sync(0xffffffffu, bchunk.y, step & 31);
+            if (lane == 0) { hin = bh; fin = bf; }
+        } else if (lane == 0) { hin = 0; fin = 0; }
+        if (lane == 0) res = r0;
+        const int8_t *ppa = pptr + (res & 0xffu) * (uint32_t) Lp;
+        const int8_t *ppb = pptr + (res >> 8) * (uint32_t) Lp;
+        uint32_t wa[W], wb[W];
+        if constexpr (K == 16) {
+            const uint4 va = *reinterpret_cast<const uint4 *>(ppa), vb = *reinterpret_cast<const uint4 *>(ppb);
+            wa[0] = va.x; wa[1] = va.y; wa[2] = va.z; wa[3] = va.w;
+            wb[0] = vb.x; wb[1] = vb.y; wb[2] = vb.z; wb[3] = vb.w;
+        } else if constexpr (K == 8) {
+            const uint2 va = *reinterpret_cast<const uint2 *>(ppa), vb = *reinterpret_cast<const uint2 *>(ppb);
+            wa[0] = va.x; wa[1] = va.y; wb[0] = vb.x; wb[1] = vb.y;
+        } else {
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+                wa[w] = reinterpret_cast<const uint32_t *>(ppa)[w];
+                wb[w] = reinterpret_cast<const uint32_t *>(ppb)[w];
+            }
+        }
+        constexpr uint32_t SEL[4] = {0xC480u, 0xD591u, 0xE6A2u, 0xF7B3u};
+#pragma unroll
+        for (int j = K - 1; j >= 0; j--) {
+            const uint32_t sc = prmt_b32(wa[j >> 2], wb[j >> 2], SEL[j & 3]);
+            Eh[j] = __viaddmax_s16x2(Eh[j], neg_ge2, H[j]);
+            const uint32_t e = __vadd2(Eh[j], neg_go2);
+            H[j] = __viaddmax_s16x2_relu(j > 0 ? H[j - 1] : hdiag_in, sc, e);
+        }
+        uint32_t f = fin;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const uint32_t fn = __viaddmax_s16x2(f, neg_ge2, H[j]);
+            H[j] = __viaddmax_s16x2(f, neg_go2, H[j]);
+            f = fn;
+        }
+#pragma unroll
+        for (int j = 0; j < K; j += 2) best = __vimax3_s16x2(best, H[j], H[j + 1]);
+        hlast = H[K - 1];
+        fout = f;
+        if (write_bnd && lane == 31 && step >= 31) bnd_wr[step - 31] = make_uint2(hlast, f);
+        hdiag_in = hin;
+    }
+    if (write_bnd) __syncwarp();
+    return best;
+}
+
+template <int K>
+__device__ __forceinline__ uint32_t sw16_tile_any(bool first, const int8_t *pptr, int Lp, const uint8_t *pa_t, const uint8_t *pb_t,
+                                                  int tla, int tlb, int ncols, int A, uint32_t neg_ge2, uint32_t neg_go2,
+                                                  const uint2 *bnd_rd, uint2 *bnd_wr, bool write_bnd, uint32_t best) {
+    if (first) return sw16_tile<K, true>(pptr, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, write_bnd, best);
+    return sw16_tile<K, false>(pptr, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, write_bnd, best);
+}
+
+// All pairs of one work item.  The query is cut into full 512-row tiles (16 rows per lane) plus one last tile whose
+// rows-per-lane flavour (4/8/12/16, item.pad_) is the smallest that covers the remainder.
+template <bool SMEM>
 __device__ __forceinline__ void sw16_item(const int8_t *prof_base, const QueryDesc &q, const WorkItem &item,
                                           const PairDesc *__restrict__ pairs, const uint8_t *__restrict__ db,
                                           const uint64_t *__restrict__ off, const int32_t *__restrict__ len, int A, int go,
                                           int ge, uint2 *bnd0, uint2 *bnd1, unsigned *next_pair_ptr, int32_t *__restrict__ out) {
-    static_assert(K % 4 == 0 && K <= 16, "K in {4,8,12,16}");
-    constexpr int W = K / 4;
-    constexpr int TILE = 32 * K;
     const int lane = threadIdx.x & 31;
     const int Lp = q.Lp;
     const uint32_t neg_ge2 = pack16(-ge, -ge), neg_go2 = pack16(-go, -go);
-    const uint32_t padres = (uint32_t) A | ((uint32_t) A << 8);
+    const int n_full = (q.qlen - 1) / 512;  // tiles of 512 rows before the last tile
+    const int k_last = (int) item.pad_;
     while (true) {
         unsigned p = 0;
         if (lane == 0) p = atomicAdd(next_pair_ptr, 2u);
@@ -654,86 +747,23 @@ __device__ __forceinline__ void sw16_item(const int8_t *prof_base, const QueryDe
         const int tla = len[ta], tlb = has_b ? len[tb] : 0;
         const uint8_t *pa_t = db + off[ta], *pb_t = db + off[tb];
         const int ncols = max(tla, tlb);
-        const int tiles = (q.qlen + TILE - 1) / TILE;
         uint32_t best = 0;
-        for (int tile = 0; tile < tiles; tile++) {
-            const int8_t *pptr = prof_base + tile * TILE + lane * K;
-            uint2 *bnd_rd = (tile & 1) ? bnd0 : bnd1;
+        for (int tile = 0; tile < n_full; tile++) {
+            const uint2 *bnd_rd = (tile & 1) ? bnd0 : bnd1;
             uint2 *bnd_wr = (tile & 1) ? bnd1 : bnd0;
-            const bool write_bnd = tile + 1 < tiles;
-            // State per row: H (previous column) and Eh = E + go.  F travels down the column as Fh = F + go.
-            // With go >= ge (host-checked) the recurrences become, per cell,
-            //   Eh' = max(Eh - ge, Hleft)            T = max(Hdiag + s, Eh' - go, 0)
-            //   H   = max(T, Fh - go)                Fh' = max(Fh - ge, T)
-            // all in place: a descending pass (E, T) then an ascending pass (F chain, one dependent op per row).
-            uint32_t H[K], Eh[K];
-#pragma unroll
-            for (int j = 0; j < K; j++) { H[j] = 0; Eh[j] = 0; }
-            uint32_t hlast = 0, fout = 0, hdiag_in = 0;
-            uint32_t res = padres, tchunk = padres;
-            uint2 bchunk = make_uint2(0, 0);
-            const int nsteps = ncols + 31;
-            for (int step = 0; step < nsteps; step++) {
-                if ((step & 31) == 0) {
-                    const int c = step + lane;
-                    const uint32_t ra = (c < tla) ? (uint32_t) pa_t[c] : (uint32_t) A;
-                    const uint32_t rb = (c < tlb) ? (uint32_t) pb_t[c] : (uint32_t) A;
-                    tchunk = ra | (rb << 8);
-                    if (tile > 0) bchunk = (c < ncols) ? bnd_rd[c] : make_uint2(0, 0);
-                }
-                const uint32_t r0 = __shfl_sync(0xffffffffu, tchunk, step & 31);
-                res = __shfl_up_sync(0xffffffffu, res, 1);
-                uint32_t hin = __shfl_up_sync(0xffffffffu, hlast, 1);
-                uint32_t fin = __shfl_up_sync(0xffffffffu, fout, 1);
-                if (tile > 0) {
-                    const uint32_t bh = __shfl_sync(0xffffffffu, bchunk.x, step & 31);
-                    const uint32_t bf = __shfl_sync(0xffffffffu, bchunk.y, step & 31);
-                    if (lane == 0) { hin = bh; fin = bf; }
-                } else if (lane == 0) { hin = 0; fin = 0; }
-                if (lane == 0) res = r0;
-                const int col = step - lane;
-                if (col >= 0 && col < ncols) {
-                    const int8_t *ppa = pptr + (size_t) (res & 0xffu) * Lp;
-                    const int8_t *ppb = pptr + (size_t) (res >> 8) * Lp;
-                    uint32_t wa[W], wb[W];
-                    if constexpr (K == 16) {
-                        const uint4 va = *reinterpret_cast<const uint4 *>(ppa), vb = *reinterpret_cast<const uint4 *>(ppb);
-                        wa[0] = va.x; wa[1] = va.y; wa[2] = va.z; wa[3] = va.w;
-                        wb[0] = vb.x; wb[1] = vb.y; wb[2] = vb.z; wb[3] = vb.w;
-                    } else if constexpr (K == 8) {
-                        const uint2 va = *reinterpret_cast<const uint2 *>(ppa), vb = *reinterpret_cast<const uint2 *>(ppb);
-                        wa[0] = va.x; wa[1] = va.y; wb[0] = vb.x; wb[1] = vb.y;
-                    } else {
-#pragma unroll
-                        for (int w = 0; w < W; w++) {
-                            wa[w] = reinterpret_cast<const uint32_t *>(ppa)[w];
-                            wb[w] = reinterpret_cast<const uint32_t *>(ppb)[w];
-                        }
-                    }
-                    constexpr uint32_t SEL[4] = {0xC480u, 0xD591u, 0xE6A2u, 0xF7B3u};
-#pragma unroll
-                    for (int j = K - 1; j >= 0; j--) {
-                        const uint32_t sc = prmt_b32(wa[j >> 2], wb[j >> 2], SEL[j & 3]);
-                        Eh[j] = __viaddmax_s16x2(Eh[j], neg_ge2, H[j]);
-                        const uint32_t e = __vadd2(Eh[j], neg_go2);
-                        H[j] = __viaddmax_s16x2_relu(j > 0 ? H[j - 1] : hdiag_in, sc, e);
-                    }
-                    uint32_t f = fin;
-#pragma unroll
-                    for (int j = 0; j < K; j++) {
-                        const uint32_t fn = __viaddmax_s16x2(f, neg_ge2, H[j]);
-                        H[j] = __viaddmax_s16x2(f, neg_go2, H[j]);
-                        f = fn;
-                    }
-#pragma unroll
-                    for (int j = 0; j < K; j += 2) best = __vimax3_s16x2(best, H[j], H[j + 1]);
-                    hlast = H[K - 1];
-                    fout = f;
-                    if (write_bnd && lane == 31) bnd_wr[col] = make_uint2(hlast, f);
-                }
-                hdiag_in = hin;
+            best = sw16_tile_any<16>(tile == 0, prof_base + tile * 512 + lane * 16, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2,
+                                     neg_go2, bnd_rd, bnd_wr, true, best);
+        }
+        {
+            const uint2 *bnd_rd = (n_full & 1) ? bnd0 : bnd1;
+            uint2 *bnd_wr = (n_full & 1) ? bnd1 : bnd0;
+            const int8_t *pl = prof_base + n_full * 512 + lane * k_last;
+            switch (k_last) {
+                case 4: best = sw16_tile_any<4>(n_full == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, false, best); break;
+                case 8: best = sw16_tile_any<8>(n_full == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, false, best); break;
+                case 12: best = sw16_tile_any<12>(n_full == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, false, best); break;
+                default: best = sw16_tile_any<16>(n_full == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, false, best); break;
             }
-            if (write_bnd) __syncwarp();
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) best = __vmaxs2(best, __shfl_xor_sync(0xffffffffu, best, o));
@@ -745,8 +775,8 @@ __device__ __forceinline__ void sw16_item(const int8_t *prof_base, const QueryDe
 }
 
 // One launch covers every query length: items carry the rows-per-lane flavour (4/8/12/16) chosen for their query.
-template <bool SMEM>
-__global__ void __launch_bounds__(SW_WARPS * 32, 6)
+template <bool SMEM, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 24 / WARPS)
 sw16_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd, const WorkItem *__restrict__ items,
             const PairDesc *__restrict__ pairs, const uint8_t *__restrict__ db, const uint64_t *__restrict__ off,
             const int32_t *__restrict__ len, int A, int go, int ge, uint2 *__restrict__ bnd, int bnd_stride,
@@ -756,7 +786,7 @@ sw16_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd,
     __shared__ unsigned next_pair;
     __shared__ unsigned cur_item;
 
-    const int warp_global = blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
+    const int warp_global = blockIdx.x * WARPS + (threadIdx.x >> 5);
     uint2 *bnd0 = bnd + (size_t) warp_global * 2 * bnd_stride;
     uint2 *bnd1 = bnd0 + bnd_stride;
     unsigned phase = 0;
@@ -787,12 +817,7 @@ sw16_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd,
             __syncthreads();
         }
         const int8_t *pb = SMEM ? (const int8_t *) smem_prof : gprof;
-        switch (item.pad_) {
-            case 4: sw16_item<4, SMEM>(pb, q, item, pairs, db, off, len, A, go, ge, bnd0, bnd1, &next_pair, out); break;
-            case 8: sw16_item<8, SMEM>(pb, q, item, pairs, db, off, len, A, go, ge, bnd0, bnd1, &next_pair, out); break;
-            case 12: sw16_item<12, SMEM>(pb, q, item, pairs, db, off, len, A, go, ge, bnd0, bnd1, &next_pair, out); break;
-            default: sw16_item<16, SMEM>(pb, q, item, pairs, db, off, len, A, go, ge, bnd0, bnd1, &next_pair, out); break;
-        }
+        sw16_item<SMEM>(pb, q, item, pairs, db, off, len, A, go, ge, bnd0, bnd1, &next_pair, out);
     }
 }
 
@@ -1225,19 +1250,10 @@ namespace {
 
 constexpr uint32_t kPairsPerItem = 8;
 
-// rows per lane of the packed kernel for a query length: least padded rows, ties to the larger tile
+// rows per lane (4/8/12/16) of the LAST tile of the packed kernel for a query length; every earlier tile is 512 rows
 int sw16_k_for(int qlen) {
-    int bestK = 16;
-    long best_rows = -1;
-    const int ks[4] = {4, 8, 12, 16};
-    for (int i = 0; i < 4; i++) {
-        const long tile = 32L * ks[i];
-        const long rows = (qlen + tile - 1) / tile * tile;
-        const long tiles = rows / tile;
-        const long cost = rows + 40 * tiles;  // a tile restart costs about a 32-step pipeline fill
-        if (best_rows < 0 || cost <= best_rows) { best_rows = cost; bestK = ks[i]; }
-    }
-    return bestK;
+    const int rem = qlen - (qlen - 1) / 512 * 512;  // 1..512 rows left for the last tile
+    return std::min(16, ((rem + 31) / 32 + 3) / 4 * 4);
 }
 
 
@@ -1248,17 +1264,23 @@ struct SwPlan {
 };
 
 // sort pairs by (query, target length desc) and cut each query's run into CTA-sized items, longest work first
-void plan_pairs(const b200_ctx *ctx, const b200_query *queries, const b200_pair *pairs, uint64_t n, const uint8_t *mask, SwPlan &plan) {
+void plan_pairs(const b200_ctx *ctx, const b200_query *queries, const b200_pair *pairs, uint64_t n, const uint8_t *mask, SwPlan &plan,
+                uint32_t pairs_per_item = kPairsPerItem) {
     std::vector<int32_t> qlens;
     { uint32_t mq = 0; for (uint64_t i = 0; i < n; i++) mq = std::max(mq, pairs[i].query); qlens.resize((size_t) mq + 1); for (uint32_t i = 0; i <= mq; i++) qlens[i] = queries[i].qlen; }
-    plan.perm.clear();
-    plan.perm.reserve(n);
-    for (uint64_t i = 0; i < n; i++) if (mask == nullptr || mask[i]) plan.perm.push_back((uint32_t) i);
+    // order: query ascending, target length descending, caller index ascending -- one 64-bit key per pair
     const int32_t *hl = ctx->h_len.data();
-    std::stable_sort(plan.perm.begin(), plan.perm.end(), [pairs, hl](uint32_t a, uint32_t b) {
-        if (pairs[a].query != pairs[b].query) return pairs[a].query < pairs[b].query;
-        return hl[pairs[a].target] > hl[pairs[b].target];
-    });
+    struct Key { uint64_t k; uint32_t i; };
+    std::vector<Key> keys;
+    keys.reserve(n);
+    for (uint64_t i = 0; i < n; i++)
+        if (mask == nullptr || mask[i]) {
+            Key e; e.k = ((uint64_t) pairs[i].query << 32) | (uint64_t) (0xffffu - (uint32_t) hl[pairs[i].target]); e.i = (uint32_t) i;
+            keys.push_back(e);
+        }
+    std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) { return a.k != b.k ? a.k < b.k : a.i < b.i; });
+    plan.perm.resize(keys.size());
+    for (size_t k = 0; k < keys.size(); k++) plan.perm[k] = keys[k].i;
     plan.items.clear();
     const uint32_t m = (uint32_t) plan.perm.size();
     uint32_t s = 0;
@@ -1266,8 +1288,8 @@ void plan_pairs(const b200_ctx *ctx, const b200_query *queries, const b200_pair 
         uint32_t e = s;
         const uint32_t qy = pairs[plan.perm[s]].query;
         while (e < m && pairs[plan.perm[e]].query == qy) e++;
-        for (uint32_t p = s; p < e; p += kPairsPerItem) {
-            WorkItem it; it.query = qy; it.p0 = p; it.p1 = std::min(e, p + kPairsPerItem); it.pad_ = (uint32_t) sw16_k_for(qlens[qy]);
+        for (uint32_t p = s; p < e; p += pairs_per_item) {
+            WorkItem it; it.query = qy; it.p0 = p; it.p1 = std::min(e, p + pairs_per_item); it.pad_ = (uint32_t) sw16_k_for(qlens[qy]);
             plan.items.push_back(it);
         }
         s = e;
@@ -1539,6 +1561,38 @@ int b200_sw_job_create(b200_ctx *ctx, const b200_query *queries, int nq, const b
 // ---- score-only batch (packed int16x2 fast path + int32 fallback) ---------------------------------------------
 namespace {
 
+template <int WARPS>
+int launch_sw16_w(b200_ctx *ctx, const QueryDesc *d_qd, const int8_t *d_pad, size_t smem, int smem_profile, const WorkItem *d_items,
+                  uint32_t n_items, const PairDesc *d_pairs, int go, int ge, uint2 *d_bnd, int bnd_stride, int32_t *d_out) {
+    int per_sm = 0;
+    if (smem_profile) {
+        CU_TRY(ctx, cudaFuncSetAttribute(sw16_kernel<true, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw16_kernel<true, WARPS>, WARPS * 32, smem) != cudaSuccess) per_sm = 1;
+    } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw16_kernel<false, WARPS>, WARPS * 32, 0) != cudaSuccess) per_sm = 1;
+    per_sm = std::max(1, per_sm);
+    const unsigned grid = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) ctx->sm_count * per_sm, n_items));
+    if (smem_profile)
+        sw16_kernel<true, WARPS><<<grid, WARPS * 32, smem, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
+                                                                         ctx->d_len, ctx->alphabet, go, ge, d_bnd, bnd_stride, n_items,
+                                                                         ctx->counter.as<unsigned>(), d_out);
+    else
+        sw16_kernel<false, WARPS><<<grid, WARPS * 32, 0, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
+                                                                       ctx->d_len, ctx->alphabet, go, ge, d_bnd, bnd_stride, n_items,
+                                                                       ctx->counter.as<unsigned>(), d_out);
+    ctx->launches++;
+    CU_TRY(ctx, cudaGetLastError());
+    return B200_OK;
+}
+
+int sw16_warps() {  // CTA width of the packed kernel (pairs per item = 2 x warps); B200_SW16_WARPS overrides for experiments
+    static int w = 0;
+    if (w == 0) {
+        const char *e = getenv("B200_SW16_WARPS");
+        w = (e != nullptr && atoi(e) == 4) ? 4 : 8;
+    }
+    return w;
+}
+
 int launch_sw16(b200_ctx *ctx, const QueryDesc *d_qd, const int8_t *d_pad, int max_Lp, const WorkItem *d_items, uint32_t n_items,
                 const PairDesc *d_pairs, int go, int ge, uint2 *d_bnd, int bnd_stride, int32_t *d_out) {
     size_t smem = (size_t) (ctx->alphabet + 1) * max_Lp;
@@ -1546,24 +1600,9 @@ int launch_sw16(b200_ctx *ctx, const QueryDesc *d_qd, const int8_t *d_pad, int m
     if (smem > (size_t) ctx->max_smem_optin - 1024) { smem = 0; smem_profile = 0; }
     CU_TRY(ctx, ctx->counter.reserve(sizeof(unsigned)));
     CU_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(unsigned), ctx->stream));
-    int per_sm = 0;
-    if (smem_profile) {
-        CU_TRY(ctx, cudaFuncSetAttribute(sw16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw16_kernel<true>, SW_WARPS * 32, smem) != cudaSuccess) per_sm = 1;
-    } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw16_kernel<false>, SW_WARPS * 32, 0) != cudaSuccess) per_sm = 1;
-    per_sm = std::max(1, per_sm);
-    const unsigned grid = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) ctx->sm_count * per_sm, n_items));
-    if (smem_profile)
-        sw16_kernel<true><<<grid, SW_WARPS * 32, smem, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off, ctx->d_len,
-                                                                     ctx->alphabet, go, ge, d_bnd, bnd_stride, n_items,
-                                                                     ctx->counter.as<unsigned>(), d_out);
-    else
-        sw16_kernel<false><<<grid, SW_WARPS * 32, 0, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off, ctx->d_len,
-                                                                   ctx->alphabet, go, ge, d_bnd, bnd_stride, n_items,
-                                                                   ctx->counter.as<unsigned>(), d_out);
-    ctx->launches++;
-    CU_TRY(ctx, cudaGetLastError());
-    return B200_OK;
+    if (sw16_warps() == 4)
+        return launch_sw16_w<4>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out);
+    return launch_sw16_w<8>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out);
 }
 
 }  // namespace
@@ -1610,7 +1649,7 @@ int b200_sw_score_job_create(b200_ctx *ctx, const b200_query *queries, int nq, c
         }
         if (!any) continue;
         SwPlan plan;
-        plan_pairs(ctx, queries, pairs, n, mask.data(), plan);
+        plan_pairs(ctx, queries, pairs, n, mask.data(), plan, klass[c] ? 2u * (uint32_t) sw16_warps() : kPairsPerItem);
         b200_job::Part *pt = new b200_job::Part();
         job->parts.push_back(pt);
         pt->K = klass[c];
@@ -1624,7 +1663,7 @@ int b200_sw_score_job_create(b200_ctx *ctx, const b200_query *queries, int nq, c
             h_pd[sidx].target = pairs[i].target; h_pd[sidx].qend = h_pd[sidx].dbend = h_pd[sidx].score = 0;
             max_cols = std::max(max_cols, ctx->h_len[pairs[i].target]);
             pt->max_Lp = std::max(pt->max_Lp, h_qd[pairs[i].query].Lp);
-            if (queries[pairs[i].query].qlen > (klass[c] ? 32 * sw16_k_for(queries[pairs[i].query].qlen) : SW_TILE)) multi = true;
+            if (queries[pairs[i].query].qlen > (klass[c] ? 512 : SW_TILE)) multi = true;
         }
         e = pt->pairs.reserve(sizeof(PairDesc) * pt->n_pairs);
         if (e == cudaSuccess) e = pt->items.reserve(sizeof(WorkItem) * pt->n_items);
@@ -1637,7 +1676,7 @@ int b200_sw_score_job_create(b200_ctx *ctx, const b200_query *queries, int nq, c
     const size_t pad_bytes = h_qd.back().rev_off + (size_t) (A + 1) * h_qd.back().Lp;
     if (e == cudaSuccess) e = job->pad.reserve(pad_bytes);
     if (e == cudaSuccess) e = job->qdesc.reserve(sizeof(QueryDesc) * nq);
-    if (e == cudaSuccess) e = job->bnd.reserve(sizeof(int2) * 2 * (size_t) job->bnd_stride * std::min<uint64_t>(max_items, sw_max_grid(ctx)) * SW_WARPS);
+    if (e == cudaSuccess) e = job->bnd.reserve(sizeof(int2) * 2 * (size_t) job->bnd_stride * std::min<uint64_t>(max_items, sw_max_grid(ctx)) * 8);
     if (e == cudaSuccess) e = cudaMemcpyAsync(job->pad.p, ctx->pad.p, pad_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(job->qdesc.p, h_qd.data(), sizeof(QueryDesc) * nq, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
