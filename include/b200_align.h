@@ -17,6 +17,8 @@
  *   b200_sw_score           the score of alignScoreEndPos (ALIGNMENT_MODE_SCORE_ONLY use, Matcher.cpp:62-144).
  *   b200_sw_score_endpos    SmithWaterman::alignScoreEndPos (StripedSmithWaterman.cpp:892-941).
  *   b200_sw_startpos        the reverse pass of SmithWaterman::alignStartPosBacktrace (:1129-1212).
+ *   b200_nucl_align         BandedNucleotideAligner::align + ksw_extz2_sse (src/alignment/BandedNucleotideAligner.cpp:73-263,
+ *                           lib/ksw2/ksw2_extz2_sse.cpp:44-285).
  *   b200_sw_align           ssw_align alignment modes 0/1 (:831-890) with the E-value/coverage gate supplied
  *                           by the caller (host double math stays in the reference: EvalueComputation.h:18-40).
  *
@@ -105,6 +107,21 @@ int b200_sw_startpos(b200_ctx *ctx, const b200_query *queries, int n_queries, co
 /* score + end for every pair, start positions for pairs with gate[i] != 0 (gate == NULL: all) */
 int b200_sw_align(b200_ctx *ctx, const b200_query *queries, int n_queries, const b200_pair *pairs, uint64_t n,
                   int gap_open, int gap_extend, const uint8_t *gate, b200_sw_aln *out);
+
+/* ---- A7: nucleotide gapped aligner ------------------------------------------------------------------ */
+/* BandedNucleotideAligner::initQuery + align (src/alignment/BandedNucleotideAligner.cpp:51-263; forward strand,
+ * wrappedScoring = false): ungapped seed on the prefilter diagonal, leftward ksw_extz2 (score only), rightward ksw_extz2
+ * with CIGAR, band 64.  The DB must have been loaded with alphabet 5 (A,C,T,G,X = 0..4, src/commons/NucleotideMatrix.cpp);
+ * scores are nucleotide.out at bit factor 1 (+2/-3; X scores 0 inside ksw2, -3 in the seed).  Sequences 1..32767 long.
+ * The reference reads one byte past each sequence when it reverses them (seq_reverse called with L,
+ * BandedNucleotideAligner.cpp:60,88); that byte is history-dependent there and is defined as X here.
+ * cigars: caller buffer; task i owns cigars[cigar_offsets[i] .. cigar_offsets[i+1]), at least 2*qlen + 72 entries,
+ * filled with out[i].n_cigar ops (len << 4 | op, op 0 = M, 1 = I (query only), 2 = D (target only)) in alignment order. */
+typedef struct { uint32_t query; uint32_t target; uint16_t diagonal; uint16_t reserved; } b200_nucl_task;
+typedef struct { int32_t score, qstart, qend, dbstart, dbend, identical, n_cigar; } b200_nucl_aln;
+int b200_nucl_align(b200_ctx *ctx, const uint8_t *query_residues, const uint64_t *query_offsets, uint32_t n_queries,
+                    const b200_nucl_task *tasks, uint64_t n, int gap_open, int gap_extend, int zdrop, b200_nucl_aln *out,
+                    uint32_t *cigars, const uint64_t *cigar_offsets);
 
 /* ---- resident-input jobs (inputs staged in HBM once, run many times; used for kernel-only timing) ----- */
 int b200_scan_job_create(b200_ctx *ctx, const b200_query *queries, int n_queries, int min_score_excl,

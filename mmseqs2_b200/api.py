@@ -64,6 +64,9 @@ class _CQuery(ctypes.Structure):
 HIT_DTYPE = np.dtype([("id", np.uint32), ("score", np.int32)])
 PAIR_DTYPE = np.dtype([("query", np.uint32), ("target", np.uint32)])
 END_DTYPE = np.dtype([("score", np.int32), ("qend", np.int32), ("dbend", np.int32), ("word", np.int32)])
+NUCL_TASK_DTYPE = np.dtype([("query", np.uint32), ("target", np.uint32), ("diagonal", np.uint16), ("reserved", np.uint16)])
+NUCL_ALN_DTYPE = np.dtype([("score", np.int32), ("qstart", np.int32), ("qend", np.int32), ("dbstart", np.int32), ("dbend", np.int32),
+                           ("identical", np.int32), ("n_cigar", np.int32)])
 ALN_DTYPE = np.dtype([("score", np.int32), ("qstart", np.int32), ("qend", np.int32), ("dbstart", np.int32),
                       ("dbend", np.int32), ("word", np.int32)])
 
@@ -297,6 +300,27 @@ class Context:
         out = np.zeros(len(pa), ALN_DTYPE)
         self._check(self.lib.b200_sw_align(self.h, cq, len(queries), _p(pa), _u64(len(pa)), go, ge, _p(g), _p(out)))
         return out
+
+    # ---- A7
+    def nucl_align(self, queries, tasks, go=5, ge=2, zdrop=40):
+        """queries: list of uint8 arrays (A,C,T,G,X = 0..4); tasks: iterable of (query, target, diagonal_u16).
+        -> (structured results, list of cigar op arrays, list of backtrace strings)"""
+        qres = np.ascontiguousarray(np.concatenate(queries), np.uint8)
+        qoff = np.zeros(len(queries) + 1, np.uint64)
+        qoff[1:] = np.cumsum([len(q) for q in queries])
+        ta = np.zeros(len(tasks), NUCL_TASK_DTYPE)
+        tarr = np.asarray(tasks, np.int64).reshape(-1, 3)
+        ta["query"], ta["target"], ta["diagonal"] = tarr[:, 0], tarr[:, 1], tarr[:, 2] & 0xffff
+        slots = np.array([2 * len(queries[int(q)]) + 72 for q in tarr[:, 0]], np.uint64)
+        coff = np.zeros(len(ta) + 1, np.uint64)
+        coff[1:] = np.cumsum(slots)
+        cig = np.zeros(int(coff[-1]) + 1, np.uint32)
+        out = np.zeros(len(ta), NUCL_ALN_DTYPE)
+        self._check(self.lib.b200_nucl_align(self.h, _p(qres), _p(qoff), ctypes.c_uint32(len(queries)), _p(ta), _u64(len(ta)), go, ge,
+                                             zdrop, _p(out), _p(cig), _p(coff)))
+        cigars = [cig[int(coff[i]):int(coff[i]) + int(out["n_cigar"][i])].copy() for i in range(len(ta))]
+        bts = ["".join("MID"[int(c & 0xf)] * int(c >> 4) for c in cg) for cg in cigars]
+        return out, cigars, bts
 
     def sw_job(self, queries, pairs, go=11, ge=1):
         cq = _cqueries(queries)

@@ -9,9 +9,7 @@
 //                              lanes, score + end position in one pass; DIR=-1 is the reverse (start position) pass
 //
 // Semantics follow the reference (cited per function); nothing here is derived from lib/libmarv.
-#include "b200_align.h"
-
-#include <cuda_runtime.h>
+#include "b200_internal.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -20,70 +18,6 @@
 #include <numeric>
 #include <string>
 #include <vector>
-
-// ------------------------------------------------------------------------------------------------
-// small helpers
-// ------------------------------------------------------------------------------------------------
-#define CU_TRY(ctx, expr)                                                                         \
-    do {                                                                                          \
-        cudaError_t e__ = (expr);                                                                 \
-        if (e__ != cudaSuccess) {                                                                 \
-            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                     \
-            return B200_ERR_CUDA;                                                                 \
-        }                                                                                         \
-    } while (0)
-
-static inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
-
-// Device scratch.  cudaMalloc/cudaFree cost hundreds of microseconds each and synchronise the device, so released
-// buffers go to a small per-process free list (best fit, bounded) instead of back to the driver; one-shot calls such as
-// b200_sw_score then run without touching the allocator after warm-up.
-struct DevPool {
-    struct Slot { void *p; size_t cap; int dev; };
-    std::mutex mu;
-    std::vector<Slot> free_list;
-    size_t held = 0;
-    static DevPool &get() { static DevPool pool; return pool; }
-    void *take(size_t n, int dev, size_t *cap_out) {
-        std::lock_guard<std::mutex> lk(mu);
-        int best = -1;
-        for (size_t i = 0; i < free_list.size(); i++)
-            if (free_list[i].dev == dev && free_list[i].cap >= n && free_list[i].cap <= 4 * n + (1u << 20) &&
-                (best < 0 || free_list[i].cap < free_list[best].cap)) best = (int) i;
-        if (best < 0) return nullptr;
-        void *p = free_list[best].p;
-        *cap_out = free_list[best].cap;
-        held -= free_list[best].cap;
-        free_list.erase(free_list.begin() + best);
-        return p;
-    }
-    void give(void *p, size_t cap, int dev) {
-        std::lock_guard<std::mutex> lk(mu);
-        if (free_list.size() >= 64 || held + cap > ((size_t) 8 << 30)) { cudaFree(p); return; }
-        Slot s = {p, cap, dev};
-        free_list.push_back(s);
-        held += cap;
-    }
-};
-
-struct DevBuf {  // grow-only device scratch
-    void *p = nullptr;
-    size_t cap = 0;
-    int dev = 0;
-    cudaError_t reserve(size_t n) {
-        if (n <= cap) return cudaSuccess;
-        release();
-        cudaGetDevice(&dev);
-        const size_t want = n + n / 4 + 256;
-        p = DevPool::get().take(want, dev, &cap);
-        if (p) return cudaSuccess;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want; else p = nullptr;
-        return e;
-    }
-    void release() { if (p) DevPool::get().give(p, cap, dev); p = nullptr; cap = 0; }
-    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
-};
 
 struct QueryDesc {     // device-side description of one query profile
     uint64_t raw_off;  // byte offset of the raw [A][qlen] int8 profile in d_raw
@@ -109,28 +43,6 @@ struct WorkItem {  // one CTA's share: pairs [p0,p1) of one query
     uint32_t pad_;
 };
 
-struct b200_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[16];
-    std::mutex mu;
-    std::string err;
-    uint64_t launches = 0;
-    int sm_count = 0, cc_major = 0, cc_minor = 0;
-    uint64_t hbm = 0;
-    int max_smem_optin = 0;
-    // resident target DB
-    uint8_t *d_res = nullptr;     // residues, every sequence 16-byte aligned and padded with code `alphabet`
-    uint64_t *d_off = nullptr;    // [n_seq] byte offset of sequence i in d_res
-    int32_t *d_len = nullptr;     // [n_seq]
-    uint32_t *d_order = nullptr;  // [n_seq] ids sorted by length descending (scan schedule)
-    std::vector<int32_t> h_len;
-    uint64_t n_seq = 0, n_res = 0;
-    int alphabet = 0;
-    int max_len = 0;
-    // scratch
-    DevBuf raw, pad, qdesc, dense, hits, nhits, pairs, items, out4, bnd, ids, diags, counts, rawout, counter;
-};
 
 // ------------------------------------------------------------------------------------------------
 // device helpers
@@ -826,7 +738,7 @@ sw16_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd,
 // ================================================================================================
 namespace {
 
-int set_err(b200_ctx *ctx, int code, const char *msg) { ctx->err = msg; return code; }
+int set_err(b200_ctx *ctx, int code, const char *msg) { return b200_set_err(ctx, code, msg); }
 
 struct ScanCfg { int G, K; };
 const ScanCfg kScanCfgs[] = {{8, 4}, {8, 8}, {8, 12}, {8, 16}, {16, 12}, {16, 16}, {16, 24}, {32, 16}, {32, 24}, {32, 32}};

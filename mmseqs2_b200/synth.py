@@ -77,3 +77,39 @@ def pack(seqs):
         off[1:] = np.cumsum([len(x) for x in seqs])
     data = np.concatenate(seqs).astype(np.uint8) if len(seqs) else np.zeros(0, np.uint8)
     return np.ascontiguousarray(data), off
+
+
+def nucl_genome(rng, n):
+    """i.i.d. A,C,T,G (codes 0..3)"""
+    return rng.integers(0, 4, n).astype(np.uint8)
+
+
+def nucl_mutate(rng, seq, subst=0.02, indel=0.002):
+    seq = np.asarray(seq, np.uint8)
+    out = seq.copy()
+    sub = rng.random(len(seq)) < subst
+    out[sub] = rng.integers(0, 4, int(sub.sum())).astype(np.uint8)
+    u = rng.random(len(seq))
+    keep = u >= indel / 2
+    pieces, last = [], 0
+    for pos in np.nonzero((u >= indel / 2) & (u < indel))[0]:
+        pieces.append(out[last:pos][keep[last:pos]])
+        pieces.append(rng.integers(0, 4, int(rng.integers(1, 4))).astype(np.uint8))
+        last = pos
+    pieces.append(out[last:][keep[last:]])
+    res = np.concatenate(pieces)
+    return res if len(res) else seq[:1].copy()
+
+
+def nucl_reads(rng, targets, n_reads, read_len=150, subst=0.02, indel=0.002):
+    """reads sampled from the targets; -> (reads, tasks[(read, target, diagonal_u16)]) with the true diagonal
+    (diagonal = query position - target position as the prefilter stores it, UngappedAlignment.cpp:423-437)"""
+    reads, tasks = [], []
+    for i in range(n_reads):
+        t = int(rng.integers(0, len(targets)))
+        tl = len(targets[t])
+        L = min(read_len, tl)
+        pos = int(rng.integers(0, tl - L + 1))
+        reads.append(nucl_mutate(rng, targets[t][pos:pos + L], subst, indel))
+        tasks.append((i, t, (-pos) & 0xffff))
+    return reads, np.array(tasks, np.int64)

@@ -111,6 +111,42 @@ class Oracle:
         return counts, raw
 
 
+NUCL_KMAT = None
+
+
+def ksw_mat(nmat):
+    """5x5 int8 matrix BandedNucleotideAligner hands to ksw2 (BandedNucleotideAligner.cpp:29-34)"""
+    return np.ascontiguousarray(nmat, np.int8)
+
+
+class KswOracle:
+    """oracle/oracle_ksw.c"""
+
+    def __init__(self, nucl_mat):
+        if not os.path.exists(ORACLE_SO):
+            build(with_ref=False)
+        self.lib = ctypes.CDLL(ORACLE_SO)
+        self.mat = np.ascontiguousarray(nucl_mat, np.int8)
+
+    def extz2(self, q, t, gapo=5, gape=2, w=64, zdrop=40, flag=0x41, cap=None):
+        q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+        ez = np.zeros(10, np.int32)
+        cap = cap or (len(q) + len(t) + 4)
+        cg = np.zeros(cap, np.uint32)
+        self.lib.orc_ksw_extz2(len(q), _p(q), len(t), _p(t), 5, _p(self.mat), gapo, gape, w, zdrop, flag, _p(ez), _p(cg), cap)
+        return ez, cg[:ez[9]]
+
+    def align(self, q, t, diagonal, gapo=5, gape=2, zdrop=40):
+        q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+        out = np.zeros(7, np.int32)
+        cap = len(q) + len(t) + 8
+        cg = np.zeros(cap, np.uint32)
+        bt = ctypes.create_string_buffer(cap)
+        self.lib.orc_banded_nucl_align(_p(q), len(q), _p(t), len(t), ctypes.c_uint16(int(diagonal) & 0xffff), _p(self.mat), _p(self.mat),
+                                       gapo, gape, zdrop, _p(out), _p(cg), cap, bt)
+        return out, cg[:out[6]], bt.value.decode()
+
+
 class Ref:
     """The reference's own hot-path code (oracle/_ref).  available() is False on boxes without the build."""
 
@@ -182,6 +218,24 @@ class Ref:
         if want_bt:
             bts = [bytes(bt[i * stride:(i + 1) * stride]).split(b"\0", 1)[0].decode() for i in range(n)]
         return out, ev, bts
+
+    def ksw_extz2(self, q, t, mat5, gapo=5, gape=2, w=64, zdrop=40, flag=0x41):
+        q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+        m = np.ascontiguousarray(mat5, np.int8)
+        out = np.zeros(11, np.int32)
+        cap = len(q) + len(t) + 4
+        cg = np.zeros(cap, np.uint32)
+        self.lib.ref_ksw_extz2(_p(q), len(q), _p(t), len(t), _p(m), gapo, gape, w, zdrop, flag, _p(out), _p(cg), cap)
+        return out, cg[:out[10]]
+
+    def nucl_align(self, q, t, diagonal, gapo=5, gape=2, zdrop=40):
+        q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+        out = np.zeros(7, np.int32)
+        cap = len(q) + len(t) + 8
+        cg = np.zeros(cap, np.uint32)
+        bt = ctypes.create_string_buffer(cap)
+        self.lib.ref_banded_nucl_align(_p(q), len(q), _p(t), len(t), int(diagonal), gapo, gape, zdrop, _p(out), _p(cg), cap, bt, cap)
+        return out, cg[:out[6]], bt.value.decode()
 
     def diag(self, q, bias_f32, tdata, toff, hit_ids, hit_diags):
         q = np.ascontiguousarray(q, np.uint8)

@@ -18,6 +18,31 @@ from mmseqs2_b200 import synth  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def make_nucl(ref):
+    """tests/golden/nucl_v1.npz: reads against genome pieces, outputs of the reference's BandedNucleotideAligner::align"""
+    rng = np.random.default_rng(5150)
+    targets = [synth.nucl_genome(rng, int(n)) for n in rng.integers(200, 3000, 40)]
+    targets[3][::17] = 4                       # X residues
+    reads, tasks = synth.nucl_reads(rng, targets, 600, 150, subst=0.04, indel=0.01)
+    for i in range(0, 600, 9):                 # off-diagonal seeds, short reads, perfect full-length copies
+        tasks[i, 2] = (int(tasks[i, 2]) + int(rng.integers(-6, 7))) & 0xffff
+    for i in range(0, 600, 50):
+        t = int(tasks[i, 1]); reads[i] = targets[t].copy(); tasks[i, 2] = 0
+    for i in range(5, 600, 40):
+        reads[i] = reads[i][:int(rng.integers(5, 40))]
+    td, to = pack_targets(targets)
+    outs, bts, cigs, coff = [], [], [], [0]
+    for (qi, ti, dg) in tasks:
+        d = int(dg) if dg < 32768 else int(dg) - 65536
+        o, cg, bt = ref.nucl_align(reads[qi], targets[ti], d)
+        outs.append(o); bts.append(bt); cigs.append(cg); coff.append(coff[-1] + len(cg))
+    qd, qo = pack_targets(reads)
+    np.savez_compressed(os.path.join(HERE, "nucl_v1.npz"), tdata=td, toff=to, qdata=qd, qoff=qo, tasks=tasks, out=np.array(outs, np.int32),
+                        cigars=np.concatenate(cigs).astype(np.uint32), cigar_off=np.array(coff, np.int64),
+                        bt=np.array(bts))
+    print("nucl fixture:", len(tasks), "alignments,", int(sum(o[6] > 1 for o in outs)), "with gaps")
+
+
 def main():
     ref = Ref()
     mat, pb, n2a = ref.matrix()
@@ -63,6 +88,7 @@ def main():
             out["q%d_cb%d_diag_raw" % (qi, cbf)] = r
         out["q%d_compbias" % qi] = f
     np.savez_compressed(os.path.join(HERE, "hotpath_v1.npz"), **out)
+    make_nucl(ref)
     print("wrote fixtures:", {k: os.path.getsize(os.path.join(HERE, k)) for k in ("blosum62.npz", "hotpath_v1.npz")})
 
 
