@@ -260,6 +260,7 @@ def main():
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--sw-queries", type=int, default=512)
     ap.add_argument("--sw-targets", type=int, default=256)
+    ap.add_argument("--nucl-reads", type=int, default=200000)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -465,6 +466,39 @@ def main():
                 sjob.close()
             except Exception as e:  # pragma: no cover
                 line["secondary"] = {"error": repr(e)}
+
+        # ---- secondary: nucleotide gapped aligner (config[4] shape in miniature: 150-bp reads vs genome pieces) ------------
+        if not args.no_secondary and world == 1:
+            try:
+                from mmseqs2_b200 import synth
+                rng = np.random.default_rng(4)
+                ntargets = [synth.nucl_genome(rng, 30000) for _ in range(200)]
+                reads, ntasks = synth.nucl_reads(rng, ntargets, args.nucl_reads, 150, subst=0.02, indel=0.002)
+                ntd, nto = synth.pack(ntargets)
+                ctx.load_db(ntd, nto, 5)
+                ctx.nucl_align(reads[:2000], ntasks[:2000])
+                t0 = time.perf_counter()
+                nout, ncig, nbt = ctx.nucl_align(reads, ntasks)
+                ndt = time.perf_counter() - t0
+                nsec = {"workload": "nucleotide gapped aligner (BASELINE config[4] shape): %d reads x 150 bp (2 %% subst, 0.2 %% indel) vs "
+                                    "%d x 30 kbp targets, nucleotide.out, gap 5/2, zdrop 40, band 64" % (len(reads), len(ntargets)),
+                        "e2e": {"value": len(reads) / ndt, "unit": "alignments/s", "includes": "H2D reads, kernel, D2H results + CIGARs, host CIGAR decode"},
+                        "aligned_residues_per_s": float((nout["qend"] - nout["qstart"] + 1).sum()) / ndt,
+                        "kernel": "nucl_align_kernel", "mean_score": float(nout["score"].mean())}
+                if not args.no_cpu:
+                    from oracle.pyoracle import Ref
+                    if Ref.available():
+                        ref = Ref()
+                        m = min(len(reads), 200000)
+                        t0 = time.perf_counter()
+                        rout = ref.nucl_align_batch(reads[:m], ntd, nto.astype(np.int64), ntasks[:m], nthreads=os.cpu_count() or 1)
+                        rdt = time.perf_counter() - t0
+                        same = bool(np.array_equal(rout[:, :5], np.stack([nout[f][:m] for f in ("score", "qstart", "qend", "dbstart", "dbend")], 1)))
+                        nsec["cpu_baseline"] = {"value": m / rdt, "unit": "alignments/s", "cores": os.cpu_count() or 1, "kind": "reference",
+                                                "sample": "%d reads in %.2f s" % (m, rdt), "results_identical_to_gpu": same}
+                line.setdefault("secondary", {})["nucl_align"] = nsec
+            except Exception as e:  # pragma: no cover
+                line.setdefault("secondary", {})["nucl_align"] = {"error": repr(e)}
 
         # ---- CPU baseline (bounded sample, rank 0, N=1 only) ---------------------------------------------------
         if not args.no_cpu and world == 1:

@@ -237,6 +237,17 @@ class Ref:
         self.lib.ref_banded_nucl_align(_p(q), len(q), _p(t), len(t), int(diagonal), gapo, gape, zdrop, _p(out), _p(cg), cap, bt, cap)
         return out, cg[:out[6]], bt.value.decode()
 
+    def nucl_align_batch(self, reads, tdata, toff, tasks, gapo=5, gape=2, zdrop=40, nthreads=8):
+        qd, qo = pack_targets(reads)
+        tq = np.ascontiguousarray(tasks[:, 0], np.uint32); tt = np.ascontiguousarray(tasks[:, 1], np.uint32)
+        dg = np.ascontiguousarray(tasks[:, 2], np.int64)
+        dg = np.where(dg >= 32768, dg - 65536, dg).astype(np.int32)
+        out = np.zeros((len(tq), 7), np.int32)
+        to = np.ascontiguousarray(toff, np.int64)
+        self.lib.ref_banded_nucl_align_batch(_p(qd), _p(qo), _p(tdata), _p(to), _p(tq), _p(tt), _p(dg), ctypes.c_int64(len(tq)), gapo, gape,
+                                             zdrop, _p(out), nthreads)
+        return out
+
     def diag(self, q, bias_f32, tdata, toff, hit_ids, hit_diags):
         q = np.ascontiguousarray(q, np.uint8)
         ids = np.ascontiguousarray(hit_ids, np.uint32)
