@@ -302,7 +302,7 @@ class Context:
         return out
 
     # ---- A7
-    def nucl_align(self, queries, tasks, go=5, ge=2, zdrop=40):
+    def nucl_align(self, queries, tasks, go=5, ge=2, zdrop=40, decode=True):
         """queries: list of uint8 arrays (A,C,T,G,X = 0..4); tasks: iterable of (query, target, diagonal_u16).
         -> (structured results, list of cigar op arrays, list of backtrace strings)"""
         qres = np.ascontiguousarray(np.concatenate(queries), np.uint8)
@@ -318,6 +318,8 @@ class Context:
         out = np.zeros(len(ta), NUCL_ALN_DTYPE)
         self._check(self.lib.b200_nucl_align(self.h, _p(qres), _p(qoff), ctypes.c_uint32(len(queries)), _p(ta), _u64(len(ta)), go, ge,
                                              zdrop, _p(out), _p(cig), _p(coff)))
+        if not decode:
+            return out, (cig, coff), None
         cigars = [cig[int(coff[i]):int(coff[i]) + int(out["n_cigar"][i])].copy() for i in range(len(ta))]
         bts = ["".join("MID"[int(c & 0xf)] * int(c >> 4) for c in cg) for cg in cigars]
         return out, cigars, bts

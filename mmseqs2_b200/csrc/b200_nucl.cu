@@ -40,9 +40,13 @@ struct Ez { int max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, n_ci
 
 // One ksw_extz2 call, executed by a full warp.  mem: zero-initialisable scratch (layout below), H: int32[Ls],
 // pmat/poff: direction bytes and per-row (st,en) for the CIGAR pass (unused when score-only).
-__device__ void ksw_extz2_warp(int qlen, const SeqView &qv, int tlen, const SeqView &tv, int8_t sc_mch, int8_t sc_mis, int q, int e,
-                               int w, int zdrop, int flag, uint8_t *mem, int32_t *H, uint8_t *pmat, int2 *poff, Ez &ez,
+template <bool SMEM>
+__device__ __forceinline__ void ksw_extz2_warp(int qlen, const SeqView &qv, int tlen, const SeqView &tv, int8_t sc_mch, int8_t sc_mis, int q, int e,
+                               int w, int zdrop, int flag, uint8_t *gmem, size_t mem_bytes_cap, uint8_t *pmat, int2 *poff, Ez &ez,
                                uint32_t *cigar, int cigar_cap) {
+    extern __shared__ __align__(16) uint8_t nucl_smem[];
+    // the ksw byte arrays + H: shared memory slice of this warp when they fit (SMEM), else the warp's global scratch slice
+    uint8_t *mem = SMEM ? nucl_smem + (size_t) (threadIdx.x >> 5) * ((mem_bytes_cap + 15) / 16 * 16) : gmem;
     const int lane = threadIdx.x & 31;
     const bool with_cigar = !(flag & EZ_SCORE_ONLY);
     const int qe = q + e;
@@ -61,6 +65,7 @@ __device__ void ksw_extz2_warp(int qlen, const SeqView &qv, int tlen, const SeqV
     int8_t *u = (int8_t *) mem, *v = u + Ls, *x = v + Ls, *y = x + Ls, *s = y + Ls;
     uint8_t *sf = (uint8_t *) (s + Ls), *qr = sf + Ls;
     const int mem_bytes = 6 * Ls + qlen_ * 16 + 32;
+    int32_t *H = reinterpret_cast<int32_t *>(mem + (mem_bytes + 15) / 16 * 16);
     for (int i = lane; i < mem_bytes; i += 32) mem[i] = 0;
     for (int i = lane; i < Ls; i += 32) H[i] = KSW_NEG_INF;
     __syncwarp();
@@ -265,6 +270,7 @@ __device__ void seed_segment(const int8_t *smat, const uint8_t *s1, const uint8_
     start = maxStart; end = maxEnd; score = maxScore;
 }
 
+template <bool SMEM>
 __global__ void __launch_bounds__(NUCL_WARPS * 32)
 nucl_align_kernel(const NuclTask *__restrict__ tasks, unsigned n_tasks, const uint8_t *__restrict__ qres,
                   const uint64_t *__restrict__ qoff, const uint8_t *__restrict__ db, const uint64_t *__restrict__ off,
@@ -280,7 +286,7 @@ nucl_align_kernel(const NuclTask *__restrict__ tasks, unsigned n_tasks, const ui
     const int lane = threadIdx.x & 31;
     const int warp_global = blockIdx.x * NUCL_WARPS + (threadIdx.x >> 5);
     uint8_t *mem = scratch + (size_t) warp_global * scratch_stride;
-    int32_t *H = reinterpret_cast<int32_t *>(mem + mem_bytes);
+    const size_t mh_cap = mem_bytes + h_bytes;   // per-warp capacity of (byte arrays + H)
     int2 *poff = reinterpret_cast<int2 *>(mem + mem_bytes + h_bytes);
     uint8_t *pmat = mem + mem_bytes + h_bytes + p_bytes;  // p_bytes here = size of the poff area; the rest is the matrix
     const int8_t sc_mch = 2, sc_mis = -3;
@@ -330,15 +336,15 @@ nucl_align_kernel(const NuclTask *__restrict__ tasks, unsigned n_tasks, const ui
         const int qStartRev = (qL - qUe) - 1, tStartRev = (tL - dUe) - 1;
         SeqView qrv = {q, qL, qStartRev, 1}, trv = {t, tL, tStartRev, 1};
         Ez ez, ezA;
-        ksw_extz2_warp(qL - qStartRev, qrv, tL - tStartRev, trv, sc_mch, sc_mis, gapo, gape, w, zdrop, EZ_SCORE_ONLY | EZ_EXTZ_ONLY, mem, H,
+        ksw_extz2_warp<SMEM>(qL - qStartRev, qrv, tL - tStartRev, trv, sc_mch, sc_mis, gapo, gape, w, zdrop, EZ_SCORE_ONLY | EZ_EXTZ_ONLY, mem, mh_cap,
                        pmat, poff, ez, cigar, cigar_cap);
         const int qStartPos = qL - (qStartRev + ez.max_q) - 1, tStartPos = tL - (tStartRev + ez.max_t) - 1;
         SeqView qfv = {q, qL, qStartPos, 0}, tfv = {t, tL, tStartPos, 0};
-        ksw_extz2_warp(qL - qStartPos, qfv, tL - tStartPos, tfv, sc_mch, sc_mis, gapo, gape, w, zdrop, EZ_EXTZ_ONLY, mem, H, pmat, poff,
+        ksw_extz2_warp<SMEM>(qL - qStartPos, qfv, tL - tStartPos, tfv, sc_mch, sc_mis, gapo, gape, w, zdrop, EZ_EXTZ_ONLY, mem, mh_cap, pmat, poff,
                        ezA, cigar, cigar_cap);
         bool reversed = false;
         if (ez.max_q > ezA.max_q && ez.max_t > ezA.max_t) {
-            ksw_extz2_warp(qL - qStartRev, qrv, tL - tStartRev, trv, sc_mch, sc_mis, gapo, gape, w, zdrop, EZ_EXTZ_ONLY, mem, H, pmat,
+            ksw_extz2_warp<SMEM>(qL - qStartRev, qrv, tL - tStartRev, trv, sc_mch, sc_mis, gapo, gape, w, zdrop, EZ_EXTZ_ONLY, mem, mh_cap, pmat,
                            poff, ezA, cigar, cigar_cap);
             reversed = true;
         }
@@ -403,8 +409,13 @@ int b200_nucl_align(b200_ctx *ctx, const uint8_t *query_residues, const uint64_t
     const size_t n_col = ((std::min<size_t>(std::min(max_q, max_t), w + 1) + 15) / 16 + 1) * 16;
     const size_t pm_bytes = round_up(rows * n_col + 64, 16);
     const size_t stride = mem_bytes + h_bytes + poff_bytes + pm_bytes;
+    const size_t smem_need = round_up(mem_bytes + h_bytes, 16) * NUCL_WARPS;
+    const bool use_smem = smem_need <= 96 * 1024;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nucl_align_kernel, NUCL_WARPS * 32, 0) != cudaSuccess) per_sm = 1;
+    if (use_smem) {
+        CU_TRY(ctx, cudaFuncSetAttribute(nucl_align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_need));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nucl_align_kernel<true>, NUCL_WARPS * 32, smem_need) != cudaSuccess) per_sm = 1;
+    } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nucl_align_kernel<false>, NUCL_WARPS * 32, 0) != cudaSuccess) per_sm = 1;
     per_sm = std::max(1, per_sm);
     const unsigned grid = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) ctx->sm_count * per_sm, (n + NUCL_WARPS - 1) / NUCL_WARPS));
     const uint64_t cig_total = cigar_offsets[n];
@@ -421,10 +432,16 @@ int b200_nucl_align(b200_ctx *ctx, const uint8_t *query_residues, const uint64_t
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_q.p, query_residues, q_total, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_qoff.p, query_offsets, sizeof(uint64_t) * ((size_t) n_queries + 1), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
-        nucl_align_kernel<<<grid, NUCL_WARPS * 32, 0, ctx->stream>>>(d_tasks.as<NuclTask>(), (unsigned) n, d_q.as<uint8_t>(), d_qoff.as<uint64_t>(),
-                                                                    ctx->d_res, ctx->d_off, ctx->d_len, gap_open, gap_extend, zdrop, w,
-                                                                    d_scratch.as<uint8_t>(), stride, mem_bytes, h_bytes, poff_bytes,
-                                                                    ctx->counter.as<unsigned>(), d_out.as<int32_t>(), d_cig.as<uint32_t>(), w + 8);
+        if (use_smem)
+            nucl_align_kernel<true><<<grid, NUCL_WARPS * 32, smem_need, ctx->stream>>>(
+                d_tasks.as<NuclTask>(), (unsigned) n, d_q.as<uint8_t>(), d_qoff.as<uint64_t>(), ctx->d_res, ctx->d_off, ctx->d_len, gap_open,
+                gap_extend, zdrop, w, d_scratch.as<uint8_t>(), stride, mem_bytes, h_bytes, poff_bytes, ctx->counter.as<unsigned>(),
+                d_out.as<int32_t>(), d_cig.as<uint32_t>(), w + 8);
+        else
+            nucl_align_kernel<false><<<grid, NUCL_WARPS * 32, 0, ctx->stream>>>(
+                d_tasks.as<NuclTask>(), (unsigned) n, d_q.as<uint8_t>(), d_qoff.as<uint64_t>(), ctx->d_res, ctx->d_off, ctx->d_len, gap_open,
+                gap_extend, zdrop, w, d_scratch.as<uint8_t>(), stride, mem_bytes, h_bytes, poff_bytes, ctx->counter.as<unsigned>(),
+                d_out.as<int32_t>(), d_cig.as<uint32_t>(), w + 8);
         ctx->launches++;
         e = cudaGetLastError();
     }
