@@ -96,13 +96,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 // P / P' are the two packings of the int16 query profile, staged in shared memory, laid out [a][c][g] as uint4 so
 // that a group's LDS.128 is conflict-free.
 // ------------------------------------------------------------------------------------------------
-template <int G, int K>
+template <int G, int K, bool TILED>
 __global__ void __launch_bounds__(256)
 ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict__ qd, const uint8_t *__restrict__ db,
                      const uint64_t *__restrict__ off, const int32_t *__restrict__ len,
                      const uint32_t *__restrict__ order, uint32_t n_seq, int A, uint8_t *__restrict__ out, uint32_t n_queries,
-                     uint32_t units_per_query, uint32_t unit_targets, unsigned *__restrict__ unit_counter) {
+                     uint32_t units_per_query, uint32_t unit_targets, unsigned *__restrict__ unit_counter,
+                     uint32_t *__restrict__ tile_bnd, uint32_t bnd_slot_words) {
     static_assert(K % 4 == 0, "K must be a multiple of 4");
+    static_assert(!TILED || G == 32, "the tiled (long-query) variant runs one target per warp");
     constexpr int C = K / 4;
     constexpr int ROW_U4 = C * G;  // uint4 per residue row
     extern __shared__ uint4 smem_u4[];
@@ -129,8 +131,18 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
     if (unit >= n_queries * units_per_query) break;
     const int qi = (int) (unit / units_per_query);
     const uint32_t chunk = unit % units_per_query;
-    if (qi != cur_q) {
-        const QueryDesc q = qd[qi];
+    // Query rows are processed in tiles of ROWS = 2*G*K (one tile unless TILED).  Tile p covers rows [p*ROWS, (p+1)*ROWS);
+    // in W-form columns it also recomputes row p*ROWS-1 from the boundary words the previous tile left in tile_bnd.
+    constexpr int ROWS = 2 * G * K;
+    const QueryDesc q = qd[qi];
+    const int n_tiles = TILED ? (q.qlen + ROWS) / ROWS : 1;   // the last tile needs room for qlen+1 rows
+    uint8_t *outq = out + (size_t) qi * n_seq;
+    const uint32_t unit_end = min(n_seq, (chunk + 1) * unit_targets);
+    uint32_t *cta_bnd = TILED ? tile_bnd + (size_t) blockIdx.x * unit_targets * bnd_slot_words : nullptr;
+  for (int tile = 0; tile < n_tiles; tile++) {
+    const int row_base = tile * ROWS;
+    if (TILED || qi != cur_q) {
+        if (TILED) __syncthreads();          // every warp is done with the previous tile's tables (and boundary words)
         const int8_t *prof = raw + q.raw_off;
         const int qlen = q.qlen;
         uint32_t *Pw = reinterpret_cast<uint32_t *>(P);
@@ -139,12 +151,13 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
         for (int idx = threadIdx.x; idx < (A + 1) * words; idx += blockDim.x) {
             const int a = idx / words, w = idx % words;
             const int gg = w / K, r = w % K, c = r >> 2, e = r & 3;
-            int s0 = 0, s1 = 0, sm1 = 0;  // rows 2w, 2w+1, 2w-1
+            const int r0 = row_base + 2 * w;
+            int s0 = 0, s1 = 0, sm1 = 0;  // rows r0, r0+1, r0-1
             if (a < A) {
                 const int8_t *pa = prof + (size_t) a * qlen;
-                if (2 * w < qlen) s0 = pa[2 * w];
-                if (2 * w + 1 < qlen) s1 = pa[2 * w + 1];
-                if (2 * w - 1 >= 0 && 2 * w - 1 < qlen) sm1 = pa[2 * w - 1];
+                if (r0 < qlen) s0 = pa[r0];
+                if (r0 + 1 < qlen) s1 = pa[r0 + 1];
+                if (r0 - 1 >= 0 && r0 - 1 < qlen) sm1 = pa[r0 - 1];
             }
             const int dst = (a * ROW_U4 + c * G + gg) * 4 + e;
             Pw[dst] = pack16(s0, s1);
@@ -154,8 +167,7 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
         cur_q = qi;
         __syncthreads();
     }
-    uint8_t *outq = out + (size_t) qi * n_seq;
-    const uint32_t unit_end = min(n_seq, (chunk + 1) * unit_targets);
+    const bool first_tile = tile == 0, last_tile = tile + 1 == n_tiles;
 
     for (uint32_t base = chunk * unit_targets + warp_in_cta * GROUPS_PER_WARP; base < unit_end; base += warps_per_cta * GROUPS_PER_WARP) {
         const uint32_t it = base + lane / G;
@@ -172,10 +184,20 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
         for (int r = 0; r < K; r++) S[r] = 0;
         uint32_t best = 0;
 
+        uint32_t *tb = TILED ? cta_bnd + (size_t) (it - chunk * unit_targets) * bnd_slot_words : nullptr;
         for (int i0 = 0; i0 < maxl; i0 += 16) {
             uint4 ch = make_uint4(padword, padword, padword, padword);
             if (i0 < tl) ch = __ldg(tp + (i0 >> 4));
             const uint32_t cw[4] = {ch.x, ch.y, ch.z, ch.w};
+            uint32_t bin[8], bout[8];            // boundary words of the 8 V-form columns of this chunk (TILED only)
+            if (TILED) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) { bin[k] = 0; bout[k] = 0; }
+                if (!first_tile && g == 0) {
+                    const uint4 b0 = *reinterpret_cast<const uint4 *>(tb + (i0 >> 1)), b1 = *reinterpret_cast<const uint4 *>(tb + (i0 >> 1) + 4);
+                    bin[0] = b0.x; bin[1] = b0.y; bin[2] = b0.z; bin[3] = b0.w; bin[4] = b1.x; bin[5] = b1.y; bin[6] = b1.z; bin[7] = b1.w;
+                }
+            }
 #pragma unroll
             for (int u = 0; u < 16; u += 2) {
                 const uint32_t wv = cw[u >> 2];
@@ -193,10 +215,11 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
                     }
 #pragma unroll
                     for (int r = 0; r < K; r += 2) best = __vimax3_s16x2(best, S[r], S[r + 1]);
+                    if (TILED) bout[u >> 1] = S[K - 1];   // rows (row_base+ROWS-2, row_base+ROWS-1) in the last lane
                 }
                 {   // odd column: W from V, shifted by one register
                     uint32_t carry = __shfl_up_sync(0xffffffffu, S[K - 1], 1, G);
-                    if (g == 0) carry = 0;
+                    if (g == 0) carry = TILED ? bin[u >> 1] : 0u;
                     const uint4 *p = Pp + a1 * ROW_U4 + g;
                     uint4 x[C];
 #pragma unroll
@@ -212,12 +235,20 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
                     for (int r = 0; r < K; r += 2) best = __vimax3_s16x2(best, S[r], S[r + 1]);
                 }
             }
+            if (TILED && !last_tile && g == G - 1 && i0 < tl) {
+                *reinterpret_cast<uint4 *>(tb + (i0 >> 1)) = make_uint4(bout[0], bout[1], bout[2], bout[3]);
+                *reinterpret_cast<uint4 *>(tb + (i0 >> 1) + 4) = make_uint4(bout[4], bout[5], bout[6], bout[7]);
+            }
         }
         int m = max((int) (best & 0xffffu), (int) (best >> 16));
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (g == 0 && it < unit_end) outq[tid] = (uint8_t) m;
+        if (g == 0 && it < unit_end) {
+            if (TILED && !first_tile) m = max(m, (int) outq[tid]);
+            outq[tid] = (uint8_t) m;
+        }
     }
+  }  // tiles
   }
 }
 
@@ -743,13 +774,13 @@ int set_err(b200_ctx *ctx, int code, const char *msg) { return b200_set_err(ctx,
 struct ScanCfg { int G, K; };
 const ScanCfg kScanCfgs[] = {{8, 4}, {8, 8}, {8, 12}, {8, 16}, {16, 12}, {16, 16}, {16, 24}, {32, 16}, {32, 24}, {32, 32}};
 
-template <int G, int K>
+template <int G, int K, bool TILED>
 cudaError_t launch_scan_cfg(b200_ctx *ctx, const int8_t *raw, const QueryDesc *qd, int nq, uint8_t *dense) {
     const size_t smem = (size_t) 2 * (ctx->alphabet + 1) * (K / 4) * G * sizeof(uint4);
-    cudaError_t e = cudaFuncSetAttribute(ungapped_scan_kernel<G, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    cudaError_t e = cudaFuncSetAttribute(ungapped_scan_kernel<G, K, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ungapped_scan_kernel<G, K>, 256, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ungapped_scan_kernel<G, K, TILED>, 256, smem);
     if (e != cudaSuccess) return e;
     per_sm = std::max(per_sm, 1);
     const uint64_t resident = (uint64_t) ctx->sm_count * per_sm;
@@ -757,15 +788,20 @@ cudaError_t launch_scan_cfg(b200_ctx *ctx, const int8_t *raw, const QueryDesc *q
     // ~16 work units per resident CTA over the whole launch, each a multiple of one CTA-wide pass over the sorted targets
     uint64_t unit_targets = ((uint64_t) ctx->n_seq * nq + resident * 16 - 1) / (resident * 16);
     unit_targets = std::max<uint64_t>(groups_per_cta, (unit_targets + groups_per_cta - 1) / groups_per_cta * groups_per_cta);
+    if (TILED) unit_targets = std::min<uint64_t>(unit_targets, 4 * groups_per_cta);   // bounds the tile-boundary scratch
     const uint32_t units_per_query = (uint32_t) ((ctx->n_seq + unit_targets - 1) / unit_targets);
     const uint64_t ctas = std::max<uint64_t>(1, std::min<uint64_t>(resident, (uint64_t) units_per_query * nq));
     e = ctx->counter.reserve(sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemsetAsync(ctx->counter.p, 0, sizeof(unsigned), ctx->stream);
+    uint32_t slot_words = 0;
+    if (TILED && e == cudaSuccess) {
+        slot_words = (uint32_t) (round_up((uint64_t) ctx->max_len, 16) / 2 + 8);
+        e = ctx->bnd.reserve(sizeof(uint32_t) * (size_t) slot_words * unit_targets * ctas);
+    }
     if (e != cudaSuccess) return e;
-    ungapped_scan_kernel<G, K><<<(unsigned) ctas, 256, smem, ctx->stream>>>(raw, qd, ctx->d_res, ctx->d_off, ctx->d_len, ctx->d_order,
-                                                                           (uint32_t) ctx->n_seq, ctx->alphabet, dense, (uint32_t) nq,
-                                                                           units_per_query, (uint32_t) unit_targets,
-                                                                           ctx->counter.as<unsigned>());
+    ungapped_scan_kernel<G, K, TILED><<<(unsigned) ctas, 256, smem, ctx->stream>>>(
+        raw, qd, ctx->d_res, ctx->d_off, ctx->d_len, ctx->d_order, (uint32_t) ctx->n_seq, ctx->alphabet, dense, (uint32_t) nq, units_per_query,
+        (uint32_t) unit_targets, ctx->counter.as<unsigned>(), TILED ? ctx->bnd.as<uint32_t>() : nullptr, slot_words);
     ctx->launches++;
     return cudaGetLastError();
 }
@@ -773,16 +809,17 @@ cudaError_t launch_scan_cfg(b200_ctx *ctx, const int8_t *raw, const QueryDesc *q
 // queries of one launch must share a (G,K) configuration; the caller groups them by capacity class
 cudaError_t launch_scan(b200_ctx *ctx, int cfg, const int8_t *raw, const QueryDesc *qd, int nq, uint8_t *dense) {
     switch (cfg) {
-        case 0: return launch_scan_cfg<8, 4>(ctx, raw, qd, nq, dense);
-        case 1: return launch_scan_cfg<8, 8>(ctx, raw, qd, nq, dense);
-        case 2: return launch_scan_cfg<8, 12>(ctx, raw, qd, nq, dense);
-        case 3: return launch_scan_cfg<8, 16>(ctx, raw, qd, nq, dense);
-        case 4: return launch_scan_cfg<16, 12>(ctx, raw, qd, nq, dense);
-        case 5: return launch_scan_cfg<16, 16>(ctx, raw, qd, nq, dense);
-        case 6: return launch_scan_cfg<16, 24>(ctx, raw, qd, nq, dense);
-        case 7: return launch_scan_cfg<32, 16>(ctx, raw, qd, nq, dense);
-        case 8: return launch_scan_cfg<32, 24>(ctx, raw, qd, nq, dense);
-        default: return launch_scan_cfg<32, 32>(ctx, raw, qd, nq, dense);
+        case 0: return launch_scan_cfg<8, 4, false>(ctx, raw, qd, nq, dense);
+        case 1: return launch_scan_cfg<8, 8, false>(ctx, raw, qd, nq, dense);
+        case 2: return launch_scan_cfg<8, 12, false>(ctx, raw, qd, nq, dense);
+        case 3: return launch_scan_cfg<8, 16, false>(ctx, raw, qd, nq, dense);
+        case 4: return launch_scan_cfg<16, 12, false>(ctx, raw, qd, nq, dense);
+        case 5: return launch_scan_cfg<16, 16, false>(ctx, raw, qd, nq, dense);
+        case 6: return launch_scan_cfg<16, 24, false>(ctx, raw, qd, nq, dense);
+        case 7: return launch_scan_cfg<32, 16, false>(ctx, raw, qd, nq, dense);
+        case 8: return launch_scan_cfg<32, 24, false>(ctx, raw, qd, nq, dense);
+        case 9: return launch_scan_cfg<32, 32, false>(ctx, raw, qd, nq, dense);
+        default: return launch_scan_cfg<32, 32, true>(ctx, raw, qd, nq, dense);   // queries longer than 2047: row tiles of 2048
     }
 }
 
@@ -790,7 +827,7 @@ int scan_cfg_for(int qlen) {
     const int n = (int) (sizeof(kScanCfgs) / sizeof(kScanCfgs[0]));
     for (int i = 0; i < n; i++)
         if (2 * kScanCfgs[i].G * kScanCfgs[i].K >= qlen + 1) return i;
-    return -1;
+    return n;  // tiled long-query variant
 }
 
 // stage raw profiles + descriptors for a set of queries; fills h_qd (pad offsets only when with_pad)
@@ -1014,12 +1051,12 @@ int b200_scan_job_create(b200_ctx *ctx, const b200_query *queries, int nq, int m
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     const int A = ctx->alphabet;
     // group queries by kernel configuration so that one launch covers one group (grid.y = group size)
-    std::vector<std::vector<int>> groups(sizeof(kScanCfgs) / sizeof(kScanCfgs[0]));
+    std::vector<std::vector<int>> groups(sizeof(kScanCfgs) / sizeof(kScanCfgs[0]) + 1);
     for (int i = 0; i < nq; i++) {
         if (queries[i].profile == nullptr || queries[i].qlen <= 0) return set_err(ctx, B200_ERR_ARG, "query without profile");
         if (queries[i].bias < 0 || queries[i].bias > 255) return set_err(ctx, B200_ERR_ARG, "profile bias outside [0,255]");
         const int c = scan_cfg_for(queries[i].qlen);
-        if (c < 0) return set_err(ctx, B200_ERR_RANGE, "b200_ungapped_scan: query longer than 2047 residues is not supported yet");
+        if (queries[i].qlen > 65535) return set_err(ctx, B200_ERR_RANGE, "b200_ungapped_scan: query longer than 65535 (maxSeqLen)");
         groups[c].push_back(i);
     }
     b200_job *job = new b200_job();

@@ -144,6 +144,26 @@ def test_long_query_tiles_and_gap_variants(ctx, oracle, submat, blosum):
         assert np.array_equal(got, oracle.sw_align(q, cb, bias, td, to, go, ge)), (go, ge)
 
 
+def test_scan_long_queries_tiled(ctx, oracle, submat, blosum):
+    """queries beyond one 2048-row tile (2048, 2049, 4095, 4096, 5000 rows) and a 1-residue query"""
+    rng = np.random.default_rng(2048)
+    bg = synth.background(blosum[1])
+    res, off = synth.random_seqs(rng, 150, bg, mean=400, sigma=0.9, lo=1, hi=6000)
+    qs = [synth.random_seqs(rng, 1, bg, mean=L, sigma=0, lo=L, hi=L, normal=True)[0] for L in (2048, 2049, 4095, 4096, 5000, 1)]
+    synth.plant_homologs(rng, res, off, qs[:5], bg, frac=0.5, subst=0.1, indel=0.01)
+    seqs = synth.split(res, off)
+    seqs[0] = qs[2].copy(); seqs[1] = qs[4][100:4900].copy()     # long identical diagonals crossing tile boundaries
+    td, to = pack_targets(seqs)
+    ctx.load_db(td, to.astype(np.uint64), 21)
+    profs = [submat.ssw_query(q) for q in qs]
+    _, _, dense = ctx.ungapped_scan(profs, want_dense=True)
+    for qi, q in enumerate(qs):
+        cb, bias = oracle.query_cb(q, True)
+        exp = oracle.ungapped(q, cb, bias, td, to)
+        assert np.array_equal(dense[qi].astype(np.int32), exp), (qi, np.nonzero(dense[qi] != exp)[0][:5])
+    assert dense[2][0] > 200 and dense[4][1] > 200
+
+
 def test_gate_and_passthrough(ctx, oracle, submat, blosum, golden, golden_db):
     qs = _queries(golden)[4:7]
     profs = [submat.ssw_query(q) for q in qs]
