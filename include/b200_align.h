@@ -17,6 +17,7 @@
  *   b200_sw_score           the score of alignScoreEndPos (ALIGNMENT_MODE_SCORE_ONLY use, Matcher.cpp:62-144).
  *   b200_sw_score_endpos    SmithWaterman::alignScoreEndPos (StripedSmithWaterman.cpp:892-941).
  *   b200_sw_startpos        the reverse pass of SmithWaterman::alignStartPosBacktrace (:1129-1212).
+ *   b200_sw_backtrace       SmithWaterman::banded_sw + computerBacktrace (:1478-1693, :1280-1308).
  *   b200_nucl_align         BandedNucleotideAligner::align + ksw_extz2_sse (src/alignment/BandedNucleotideAligner.cpp:73-263,
  *                           lib/ksw2/ksw2_extz2_sse.cpp:44-285).
  *   b200_sw_align           ssw_align alignment modes 0/1 (:831-890) with the E-value/coverage gate supplied
@@ -107,6 +108,21 @@ int b200_sw_startpos(b200_ctx *ctx, const b200_query *queries, int n_queries, co
 /* score + end for every pair, start positions for pairs with gate[i] != 0 (gate == NULL: all) */
 int b200_sw_align(b200_ctx *ctx, const b200_query *queries, int n_queries, const b200_pair *pairs, uint64_t n,
                   int gap_open, int gap_extend, const uint8_t *gate, b200_sw_aln *out);
+
+/* ---- A6: CIGAR / backtrace of protein alignments (alignment modes 2 and 3) ------------------------------- */
+/* banded_sw + computerBacktrace (src/alignment/StripedSmithWaterman.cpp:1478-1693, 1280-1308) for alignments whose score,
+ * start and end are known (alns[i] from b200_sw_align / b200_sw_startpos; entries with dbend < 0 or qstart < 0 are skipped).
+ * query_seqs[q]: numeric residues of query q (for the identity count).  The substitution scores are read from the same
+ * [A][qlen] profile as everywhere else, i.e. mat[target][query]; banded_sw reads mat[query][target] -- identical for the
+ * symmetric matrices MMseqs2 ships.  cigars: task i owns cigars[cigar_offsets[i] .. cigar_offsets[i+1]), at least
+ * (qend-qstart+1) + (dbend-dbstart+1) + 2 entries; ops are len << 4 | op (0 = M, 1 = I query only, 2 = D target only) in
+ * alignment order; the reference's backtrace string is their expansion.  ok == 0 reproduces the reference's
+ * "Trace back error" outcome (no CIGAR).  Word-mode alignments: the official binary uses the Rust block-aligner here
+ * (SURVEY.md T7); this reproduces the reference's own fallback path (:879-882). */
+typedef struct { int32_t n_cigar, identical, bt_len, ok; } b200_sw_bt;
+int b200_sw_backtrace(b200_ctx *ctx, const b200_query *queries, const uint8_t *const *query_seqs, int n_queries,
+                      const b200_pair *pairs, uint64_t n, int gap_open, int gap_extend, const b200_sw_aln *alns, b200_sw_bt *out,
+                      uint32_t *cigars, const uint64_t *cigar_offsets);
 
 /* ---- A7: nucleotide gapped aligner ------------------------------------------------------------------ */
 /* BandedNucleotideAligner::initQuery + align (src/alignment/BandedNucleotideAligner.cpp:51-263; forward strand,

@@ -301,6 +301,30 @@ class Context:
         self._check(self.lib.b200_sw_align(self.h, cq, len(queries), _p(pa), _u64(len(pa)), go, ge, _p(g), _p(out)))
         return out
 
+    # ---- A6
+    def sw_backtrace(self, queries, query_seqs, pairs, alns, go=11, ge=1):
+        """-> (structured results, list of backtrace strings); alns as returned by sw_align"""
+        cq = _cqueries(queries)
+        pa = pairs if getattr(pairs, "dtype", None) == PAIR_DTYPE else self._pairs(pairs)
+        alns = np.ascontiguousarray(alns, ALN_DTYPE)
+        seqs = [np.ascontiguousarray(x, np.uint8) for x in query_seqs]
+        ptrs = (_vp * len(seqs))(*[x.ctypes.data for x in seqs])
+        qlen = np.array([len(x) for x in seqs], np.int64)
+        tl = np.maximum(alns["dbend"] - alns["dbstart"] + 1, 0).astype(np.int64)
+        ql = np.maximum(alns["qend"] - alns["qstart"] + 1, 0).astype(np.int64)
+        slots = (ql + tl + 2).astype(np.uint64)
+        coff = np.zeros(len(pa) + 1, np.uint64)
+        coff[1:] = np.cumsum(slots)
+        cig = np.zeros(int(coff[-1]) + 1, np.uint32)
+        out = np.zeros(len(pa), np.dtype([("n_cigar", np.int32), ("identical", np.int32), ("bt_len", np.int32), ("ok", np.int32)]))
+        self._check(self.lib.b200_sw_backtrace(self.h, cq, ptrs, len(queries), _p(pa), _u64(len(pa)), go, ge, _p(alns), _p(out), _p(cig),
+                                               _p(coff)))
+        bts = []
+        for i in range(len(pa)):
+            cg = cig[int(coff[i]):int(coff[i]) + int(out["n_cigar"][i])]
+            bts.append("".join("MID"[int(c & 0xf)] * int(c >> 4) for c in cg))
+        return out, bts
+
     # ---- A7
     def nucl_align(self, queries, tasks, go=5, ge=2, zdrop=40, decode=True):
         """queries: list of uint8 arrays (A,C,T,G,X = 0..4); tasks: iterable of (query, target, diagonal_u16).

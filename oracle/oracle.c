@@ -269,3 +269,113 @@ void orc_diag_score_batch(const int16_t *mat, int A, const uint8_t *q, int qL, c
         counts[i] = (uint8_t) ORC_MIN(255, s);
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * A6: CIGAR of an alignment whose score and end points are known.
+ * SmithWaterman::banded_sw, StripedSmithWaterman.cpp:1478-1693 (band |dbLen-qLen|+1, doubled until the banded score
+ * reaches the known score; three direction bytes per cell; trace back from the bottom-right corner) and
+ * computerBacktrace :1280-1308 (expansion to an M/I/D string, identity count).
+ * The h/e rows and the direction bytes persist across band doublings exactly as the reference's realloc'ed buffers do.
+ * bt receives the backtrace string (NUL-terminated, cap bytes); returns its length, -1 on "trace back error".
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { int band; } orc_band;
+static inline int band_u(int band, int i, int j) { int x = i - band; x = x > 0 ? x : 0; return j - x + 1; }
+static inline int64_t band_d(int band, int i, int j, int p) { int x = i - band; x = x > 0 ? x : 0; return (int64_t) (j - x) * 3 + p; }
+
+int orc_sw_backtrace(const int16_t *mat, int A, const uint8_t *q, const int8_t *cb, const uint8_t *t, int qStart, int qEnd,
+                     int dbStart, int dbEnd, int score, int go, int ge, char *bt, int cap, int32_t *identical) {
+    const uint8_t *qs = q + qStart, *ts = t + dbStart;
+    const int8_t *cbs = cb + qStart;
+    const int q_len = qEnd - qStart + 1, db_len = dbEnd - dbStart + 1;
+    int band = abs(db_len - q_len) + 1;
+    /* generous fixed buffers: the band at most doubles past max(q_len, db_len) */
+    int max_band = band;
+    while (max_band < q_len + db_len) max_band *= 2;
+    max_band *= 2;
+    const size_t rowcap = (size_t) max_band * 2 + 8;
+    int32_t *hb = (int32_t *) calloc(rowcap, sizeof(int32_t)), *eb = (int32_t *) calloc(rowcap, sizeof(int32_t)),
+            *hc = (int32_t *) calloc(rowcap, sizeof(int32_t));
+    size_t dcap = 0;
+    int8_t *direction = NULL, *dl = NULL;
+    int64_t width = 0, width_d = 0;
+    int max = 0;
+    do {
+        width = (int64_t) band * 2 + 3; width_d = (int64_t) band * 2 + 1;
+        const size_t need = (size_t) (width_d * q_len * 3) + 16;
+        if (need > dcap) {
+            int8_t *nd = (int8_t *) calloc(need, 1);
+            if (direction) { memcpy(nd, direction, dcap); free(direction); }
+            direction = nd; dcap = need;
+        }
+        for (int64_t j = 1; j < width - 1; j++) hb[j] = 0;
+        for (int i = 0; i < q_len; i++) {
+            int beg = i - band; if (beg < 0) beg = 0;
+            int end = i + band; if (end > db_len - 1) end = db_len - 1;
+            const int64_t edge = end + 1 < width - 1 ? end + 1 : width - 1;
+            int f = 0, u = 0;
+            hb[0] = eb[0] = hb[edge] = eb[edge] = hc[0] = 0;
+            dl = direction + width_d * i * 3;
+            for (int j = beg; j <= end; j++) {
+                u = band_u(band, i, j);
+                const int e_ = band_u(band, i - 1, j), b = band_u(band, i, j - 1), d = band_u(band, i - 1, j - 1);
+                const int64_t de = band_d(band, i, j, 0), df = band_d(band, i, j, 1), dh = band_d(band, i, j, 2);
+                int t1 = (i == 0) ? -go : hb[e_] - go;
+                int t2 = (i == 0) ? -ge : eb[e_] - ge;
+                eb[u] = t1 > t2 ? t1 : t2;
+                dl[de] = t1 > t2 ? 3 : 2;
+                t1 = hc[b] - go; t2 = f - ge;
+                f = t1 > t2 ? t1 : t2;
+                dl[df] = t1 > t2 ? 5 : 4;
+                const int f1 = f > 0 ? f : 0, e1 = eb[u] > 0 ? eb[u] : 0;
+                t1 = e1 > f1 ? e1 : f1;
+                t2 = hb[d] + mat[(size_t) qs[i] * A + ts[j]] + cbs[i];
+                hc[u] = t1 > t2 ? t1 : t2;
+                if (hc[u] > max) max = hc[u];
+                if (t1 <= t2) dl[dh] = 1; else dl[dh] = e1 > f1 ? dl[de] : dl[df];
+            }
+            for (int j = 1; j <= u; j++) hb[j] = hc[j];
+        }
+        band *= 2;
+    } while (max < score);
+    band /= 2;
+    /* trace back */
+    int i = q_len - 1, j = db_len - 1, e = 0, n = 0, state = 2, ok = 1;
+    char op = 'M', prev_op = 'M';
+    uint32_t *c = (uint32_t *) malloc(((size_t) q_len + db_len + 4) * sizeof(uint32_t));
+    while (i > 0 || j > 0) {
+        const int64_t idx = band_d(band, i, j, state);
+        switch (dl[idx]) {
+            case 1: --i; --j; state = 2; dl -= width_d * 3; op = 'M'; break;
+            case 2: --i; state = 0; dl -= width_d * 3; op = 'I'; break;
+            case 3: --i; state = 2; dl -= width_d * 3; op = 'I'; break;
+            case 4: --j; state = 1; op = 'D'; break;
+            case 5: --j; state = 2; op = 'D'; break;
+            default: ok = 0; break;
+        }
+        if (!ok) break;
+        if (op == prev_op) ++e;
+        else { c[n++] = (uint32_t) e << 4 | (prev_op == 'M' ? 0u : prev_op == 'I' ? 1u : 2u); prev_op = op; e = 1; }
+    }
+    int len = -1;
+    if (ok) {
+        if (op == 'M') c[n++] = (uint32_t) (e + 1) << 4;
+        else { c[n++] = (uint32_t) e << 4 | (op == 'I' ? 1u : 2u); c[n++] = 1u << 4; }
+        /* the list was built end -> start: read it backwards (computerBacktrace) */
+        int ids = 0, tp = dbStart, qp = qStart;
+        len = 0;
+        for (int k = n - 1; k >= 0; k--) {
+            const uint32_t L = c[k] >> 4, o = c[k] & 0xf;
+            for (uint32_t r = 0; r < L; r++) {
+                if (o == 0) { ids += t[tp] == q[qp]; ++tp; ++qp; }
+                else if (o == 1) ++qp;
+                else ++tp;
+                if (len < cap - 1) bt[len] = "MID"[o];
+                len++;
+            }
+        }
+        if (len < cap) bt[len] = 0; else bt[cap - 1] = 0;
+        *identical = ids;
+    } else { bt[0] = 0; *identical = 0; }
+    free(c); free(direction); free(hb); free(eb); free(hc);
+    return len;
+}

@@ -100,6 +100,16 @@ class Oracle:
                                     ctypes.c_int64(n), go, ge, _p(g), _p(out), nthreads)
         return out
 
+    def backtrace(self, q, cb, t, aln, go=11, ge=1):
+        """aln = (score, qstart, qend, dbstart, dbend, ...) -> (backtrace string or None on trace-back error, identical)"""
+        q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+        buf = ctypes.create_string_buffer(len(q) + len(t) + 8)
+        ids = ctypes.c_int32()
+        self.lib.orc_sw_backtrace.restype = ctypes.c_int
+        n = self.lib.orc_sw_backtrace(_p(self.mat), self.A, _p(q), _p(cb), _p(t), int(aln[1]), int(aln[2]), int(aln[3]), int(aln[4]),
+                                      int(aln[0]), go, ge, buf, len(buf), ctypes.byref(ids))
+        return (buf.value.decode() if n >= 0 else None), ids.value
+
     def diag(self, q, cb4, tdata, toff, hit_ids, hit_diags):
         q = np.ascontiguousarray(q, np.uint8)
         ids = np.ascontiguousarray(hit_ids, np.uint32)

@@ -74,6 +74,10 @@ def main():
             out[key + "endpos"] = ref.sw_score_endpos(q, cbf, td, to)
             aln, ev, _ = ref.ssw_align(q, cbf, td, to, mode=1)
             out[key + "align"] = aln[:, :6]
+            if cbf == 1:   # alignment mode 2: backtrace string + identity count (banded_sw + computerBacktrace)
+                aln2, _, bts = ref.ssw_align(q, cbf, td, to, mode=2, want_bt=True)
+                out[key + "bt"] = np.array(bts)
+                out[key + "ident"] = aln2[:, 6]
         # per-diagonal scorer
         nh = 1500
         ids = rng.integers(0, len(tg), nh).astype(np.uint32)

@@ -80,6 +80,28 @@ def test_packed_score_matches_reference_outputs(ctx, golden, golden_db, submat):
     assert one[0] == golden["q0_cb1_endpos"][5, 0]
 
 
+def test_backtrace_matches_reference_outputs(ctx, golden, golden_db, submat):
+    """A6: b200_sw_backtrace == the reference's backtrace string and identity count (alignment mode 2) for the fixture"""
+    qs = _queries(golden)
+    n = len(golden["toff"]) - 1
+    pairs = np.array([(qi, t) for qi in range(len(qs)) for t in range(n)], np.uint32)
+    profs = [submat.ssw_query(q) for q in qs]
+    aln = ctx.sw_align(profs, pairs)
+    out, bts = ctx.sw_backtrace(profs, qs, pairs, aln)
+    checked = 0
+    for qi in range(len(qs)):
+        exp_bt, exp_id = golden["q%d_cb1_bt" % qi], golden["q%d_cb1_ident" % qi]
+        for t in range(n):
+            k = qi * n + t
+            if aln["dbend"][k] == -1:
+                assert out["n_cigar"][k] == 0
+                continue
+            assert out["ok"][k] == 1 and bts[k] == str(exp_bt[t]) and out["identical"][k] == exp_id[t], (qi, t)
+            assert out["bt_len"][k] == len(bts[k])
+            checked += 1
+    assert checked > 2000
+
+
 def test_diag_matches_reference_outputs(ctx, golden, golden_db, submat):
     for qi, q in enumerate(_queries(golden)):
         ids, dg = golden["q%d_diag_ids" % qi], golden["q%d_diag_dg" % qi]

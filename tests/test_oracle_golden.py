@@ -56,3 +56,21 @@ def test_diag_scores(golden, oracle):
             assert np.array_equal(r, golden["q%d_cb%d_diag_raw" % (i, cbf)]), (i, cbf)
             clamped += int((c == 255).sum())
     assert clamped > 0  # 255 clamp exercised (T2)
+
+
+def test_backtrace_and_identities(golden, oracle):
+    """A6: banded_sw + computerBacktrace (alignment mode 2 of the reference) for every aligned pair of the fixture"""
+    td, to = golden["tdata"], golden["toff"]
+    n_gapped = 0
+    for i, q in enumerate(_queries(golden)):
+        cb, bias = oracle.query_cb(q, True)
+        aln = golden["q%d_cb1_align" % i]
+        bts, ident = golden["q%d_cb1_bt" % i], golden["q%d_cb1_ident" % i]
+        for k in range(len(aln)):
+            if aln[k, 4] == -1:
+                continue
+            t = td[int(to[k]):int(to[k + 1])]
+            bt, ids = oracle.backtrace(q, cb, t, aln[k])
+            assert bt == str(bts[k]) and ids == ident[k], (i, k)
+            n_gapped += ("I" in bt) or ("D" in bt)
+    assert n_gapped > 100
