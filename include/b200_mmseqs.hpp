@@ -20,6 +20,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <string>
 #include <vector>
 
 #include "b200_align.h"
@@ -170,6 +171,8 @@ struct s_align {  // the fields of StripedSmithWaterman.h:59-74 this path produc
     int32_t dbStartPos1, dbEndPos1, qStartPos1, qEndPos1;
     float qCov, tCov;
     int word;
+    uint32_t identicalAACnt;   // alignment modes >= 2
+    std::string backtrace;     // M/I/D string of computerBacktrace, alignment modes >= 2
 };
 
 class SmithWaterman {
@@ -182,6 +185,7 @@ public:
     // ssw_init(const Sequence* q, const int8_t* mat, const BaseMatrix* m)   StripedSmithWaterman.cpp:1364-1476
     int ssw_init(const unsigned char *numSequence, int L) {
         qlen_ = L;
+        seq_.assign(numSequence, numSequence + L);
         cb_.assign(L, 0);
         if (biasCorr_) {
             tmp_.resize(L);
@@ -208,6 +212,7 @@ public:
     //      such hits fail Alignment::checkCriteria anyway, Alignment.cpp:389)
     //   3. end positions of the survivors; gateCov(qCov, tCov, userData) as hasLowerCoverage does with start 0
     //   4. start positions of the remaining ones (alignmentMode >= 1)
+    //   5. CIGAR / identities of those (alignmentMode >= 2): banded_sw + computerBacktrace on the device
     // dbLen[i] is needed for the coverage values only.  out[i].dbEndPos1 == -1 marks "no residue aligned" or "gated out".
     typedef bool (*GateScore)(uint32_t score1, void *userData);
     typedef bool (*GateCov)(float qCov, float tCov, void *userData);
@@ -227,7 +232,7 @@ public:
         for (size_t i = 0; i < n; i++) {
             s_align &r = out[i];
             r.score1 = (uint32_t) score[i]; r.dbStartPos1 = -1; r.qStartPos1 = -1; r.dbEndPos1 = -1; r.qEndPos1 = qlen_ - 1;
-            r.qCov = 0; r.tCov = 0; r.word = (score[i] + bias_ >= 255) ? 1 : 0;
+            r.qCov = 0; r.tCov = 0; r.word = (score[i] + bias_ >= 255) ? 1 : 0; r.identicalAACnt = 0; r.backtrace.clear();
             if (score[i] > 0 && (gateScore == NULL || gateScore(r.score1, userData))) { sub.push_back(pairs[i]); idx.push_back(i); }
         }
         if (sub.empty()) { targets_.clear(); return B200_OK; }
@@ -257,6 +262,30 @@ public:
                 r.qCov = computeCov(r.qStartPos1, r.qEndPos1, qlen_);
                 r.tCov = computeCov(r.dbStartPos1, r.dbEndPos1, dbLen[idx2[k]]);
             }
+            if (alignmentMode >= 2) {   // alignStartPosBacktrace generates the CIGAR unless the start-based coverage fails (:1213-1218)
+                std::vector<b200_pair> sub3; std::vector<b200_sw_aln> aln3; std::vector<size_t> idx3;
+                std::vector<uint64_t> coff(1, 0);
+                for (size_t k = 0; k < sub2.size(); k++) {
+                    const s_align &r = out[idx2[k]];
+                    if (gateCov != NULL && !gateCov(r.qCov, r.tCov, userData)) continue;
+                    sub3.push_back(sub2[k]); aln3.push_back(aln[k]); idx3.push_back(idx2[k]);
+                    coff.push_back(coff.back() + (uint64_t) (aln[k].qend - aln[k].qstart + 1) + (uint64_t) (aln[k].dbend - aln[k].dbstart + 1) + 2);
+                }
+                if (!sub3.empty()) {
+                    std::vector<b200_sw_bt> bt(sub3.size());
+                    std::vector<uint32_t> cig(coff.back() + 1);
+                    const uint8_t *seqp = seq_.data();
+                    rc = b200_sw_backtrace(dev_->ctx(), &q, &seqp, 1, sub3.data(), sub3.size(), gapOpen, gapExtend, aln3.data(), bt.data(),
+                                           cig.data(), coff.data());
+                    if (rc != B200_OK) return rc;
+                    for (size_t k = 0; k < sub3.size(); k++) {
+                        s_align &r = out[idx3[k]];
+                        r.identicalAACnt = (uint32_t) bt[k].identical;
+                        r.backtrace.reserve((size_t) bt[k].bt_len);
+                        for (int c = 0; c < bt[k].n_cigar; c++) r.backtrace.append((size_t) (cig[coff[k] + c] >> 4), "MID"[cig[coff[k] + c] & 0xfu]);
+                    }
+                }
+            }
         }
         targets_.clear();
         return B200_OK;
@@ -275,6 +304,7 @@ private:
     int qlen_, bias_;
     std::vector<float> tmp_;
     std::vector<int8_t> cb_, profile_;
+    std::vector<uint8_t> seq_;
     std::vector<uint32_t> targets_;
 };
 

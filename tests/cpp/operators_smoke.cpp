@@ -45,10 +45,11 @@ int main(int argc, char **argv) {
     if (sw.ssw_init(q.data(), qlen) != 0) return 5;
     for (int i = 0; i < nT; i++) sw.addTarget((uint32_t) i);
     std::vector<b200::s_align> aln;
-    if (sw.flush(dbLen.data(), 11, 1, 1, gate_score, NULL, &minScore, aln) != B200_OK) { fprintf(stderr, "%s\n", dev.error()); return 6; }
+    if (sw.flush(dbLen.data(), 11, 1, 2, gate_score, NULL, &minScore, aln) != B200_OK) { fprintf(stderr, "%s\n", dev.error()); return 6; }
     for (int i = 0; i < nT; i++) {
         out.push_back((int32_t) aln[i].score1); out.push_back(aln[i].qStartPos1); out.push_back(aln[i].qEndPos1);
         out.push_back(aln[i].dbStartPos1); out.push_back(aln[i].dbEndPos1); out.push_back(aln[i].word);
+        out.push_back((int32_t) aln[i].identicalAACnt); out.push_back((int32_t) aln[i].backtrace.size());
     }
     // --- Marv-style scan with the profile ungappedprefilter.cpp:195-203 builds
     std::vector<int8_t> pssm((size_t) A * qlen);

@@ -38,7 +38,8 @@ def test_operator_mirror_matches_oracle(tmp_path, built_lib, oracle, blosum):
         off.astype(np.uint64).tofile(f); res.tofile(f); q.tofile(f); ids.tofile(f); dg.tofile(f)
     subprocess.check_call([exe, inp, outp])
     out = np.fromfile(outp, np.int32)
-    aln = out[:300 * 6].reshape(300, 6)
+    full = out[:300 * 8].reshape(300, 8)
+    aln = full[:, :6]
     cb, bias = oracle.query_cb(q, True)
     to = off.astype(np.int64)
     exp = oracle.sw_align(q, cb, bias, res, to)
@@ -47,7 +48,12 @@ def test_operator_mirror_matches_oracle(tmp_path, built_lib, oracle, blosum):
     assert np.array_equal(aln[:, 0], exp[:, 0])
     assert np.array_equal(aln[passed], exp[passed])
     assert (aln[~passed][:, [1, 3, 4]] == -1).all()
-    rest = out[300 * 6:]
+    for k in np.nonzero(passed)[0]:   # alignment mode 2: identities + backtrace length from the device CIGAR
+        if exp[k, 4] == -1:
+            continue
+        bt, ids = oracle.backtrace(q, cb, res[int(to[k]):int(to[k + 1])], exp[k])
+        assert full[k, 6] == ids and full[k, 7] == len(bt), k
+    rest = out[300 * 8:]
     n_scan = rest[0]
     scan = rest[1:101].reshape(50, 2)
     dense = oracle.ungapped(q, cb, bias, res, to)
