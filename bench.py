@@ -437,6 +437,10 @@ def main():
                 sw_ms = ctx.event_elapsed_ms(6, 7)
                 ends = sjob.fetch()
                 sjob.close()
+                t0 = time.perf_counter()
+                ends_host = ctx.sw_score_endpos(sprofs, spairs)   # packed score pass + packed FIND pass, host buffers
+                se_e2e = time.perf_counter() - t0
+                assert np.array_equal(ends_host, ends)
                 sclk = clk.stop()
                 assert np.array_equal(sc_job, ends["score"]) and np.array_equal(sc_host, sc_job)
                 sclk_mhz = sclk.get("sm_mhz") or clk_mhz
@@ -446,7 +450,9 @@ def main():
                        "ms": f_ms, "aligned_residues_per_s": resid / (f_ms / 1e3),
                        "e2e": {"value": sw_cells / 1e9 / f_e2e, "unit": METRIC,
                                "h2d_bytes": int(sum(p.profile.nbytes for p in sprofs) + spairs.nbytes), "d2h_bytes": int(4 * len(spairs))},
-                       "score_endpos": {"value": sw_cells / 1e9 / (sw_ms / 1e3), "unit": METRIC, "kernel": "sw32_kernel<1>", "ms": sw_ms},
+                       "score_endpos": {"value": sw_cells / 1e9 / (sw_ms / 1e3), "unit": METRIC, "kernel": "sw32_kernel<1>", "ms": sw_ms,
+                                        "e2e": {"value": sw_cells / 1e9 / se_e2e, "unit": METRIC,
+                                                "path": "b200_sw_score_endpos: sw16 score pass + sw16 FIND pass (end positions), host buffers"}},
                        "word_mode_pairs": int(ends["word"].sum()), "clocks": sclk}
                 dpx16 = rates.get("viaddmax_s16x2")
                 if dpx16:

@@ -577,10 +577,15 @@ __device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t se
 
 // One query tile (32*K rows starting at row `row_base`) against the two targets of a warp task, all columns.
 // FIRST: tile 0 (no boundary row to read).  Returns the running packed maximum.
-template <int K, bool FIRST>
+// FIND (end positions for known scores): target = packed scores of the two targets (0xFFFF = half not wanted); every lane
+// records, per half, the first column in which one of its rows equals the score and the smallest such row
+// (key = col << 16 | row); the scan stops 31 steps after every wanted half has been seen somewhere in the warp.
+template <int K, bool FIRST, bool FIND>
 __device__ __forceinline__ uint32_t sw16_tile(const int8_t *pptr, int Lp, const uint8_t *pa_t, const uint8_t *pb_t, int tla,
                                               int tlb, int ncols, int A, uint32_t neg_ge2, uint32_t neg_go2,
-                                              const uint2 *bnd_rd, uint2 *bnd_wr, bool write_bnd, uint32_t best) {
+                                              const uint2 *bnd_rd, uint2 *bnd_wr, bool write_bnd, uint32_t best,
+                                              uint32_t target = 0, int row_base = 0, uint32_t *key_lo = nullptr,
+                                              uint32_t *key_hi = nullptr) {
     static_assert(K % 4 == 0 && K <= 16, "K in {4,8,12,16}");
     constexpr int W = K / 4;
     const int lane = threadIdx.x & 31;
@@ -599,6 +604,8 @@ __device__ __forceinline__ uint32_t sw16_tile(const int8_t *pptr, int Lp, const 
     uint32_t res = padres, tchunk = padres;
     uint2 bchunk = make_uint2(0, 0);
     const int nsteps = ncols + 31;
+    int stop_at = 0x7fffffff;
+    const bool want_lo = FIND && (target & 0xffffu) != 0xffffu, want_hi = FIND && (target >> 16) != 0xffffu;
     for (int step = 0; step < nsteps; step++) {
         if ((step & 31) == 0) {
             const int c = step + lane;
@@ -649,28 +656,62 @@ __device__ __forceinline__ uint32_t sw16_tile(const int8_t *pptr, int Lp, const 
             H[j] = __viaddmax_s16x2(f, neg_go2, H[j]);
             f = fn;
         }
+        if (!FIND) {
 #pragma unroll
-        for (int j = 0; j < K; j += 2) best = __vimax3_s16x2(best, H[j], H[j + 1]);
+            for (int j = 0; j < K; j += 2) best = __vimax3_s16x2(best, H[j], H[j + 1]);
+        } else {
+            uint32_t cm = 0;
+#pragma unroll
+            for (int j = 0; j < K; j += 2) cm = __vimax3_s16x2(cm, H[j], H[j + 1]);
+            const uint32_t dx = cm ^ target;
+            const bool mlo = (dx & 0xffffu) == 0 && *key_lo == 0xffffffffu;
+            const bool mhi = (dx >> 16) == 0 && *key_hi == 0xffffffffu;
+            if (mlo || mhi) {          // rare: a lane reaches the final score
+                const int col = step - lane;
+                if (mlo) {
+                    int jr = K - 1;
+#pragma unroll
+                    for (int j = K - 2; j >= 0; j--) if ((H[j] & 0xffffu) == (target & 0xffffu)) jr = j;
+                    *key_lo = ((uint32_t) col << 16) | (uint32_t) (row_base + lane * K + jr);
+                }
+                if (mhi) {
+                    int jr = K - 1;
+#pragma unroll
+                    for (int j = K - 2; j >= 0; j--) if ((H[j] >> 16) == (target >> 16)) jr = j;
+                    *key_hi = ((uint32_t) col << 16) | (uint32_t) (row_base + lane * K + jr);
+                }
+            }
+            if (stop_at == 0x7fffffff) {
+                const bool seen_lo = !want_lo || __any_sync(0xffffffffu, *key_lo != 0xffffffffu);
+                const bool seen_hi = !want_hi || __any_sync(0xffffffffu, *key_hi != 0xffffffffu);
+                if (seen_lo && seen_hi) stop_at = step + 31;
+            }
+        }
         hlast = H[K - 1];
         fout = f;
         if (write_bnd && lane == 31 && step >= 31) bnd_wr[step - 31] = make_uint2(hlast, f);
         hdiag_in = hin;
+        if (FIND && step >= stop_at) break;
     }
     if (write_bnd) __syncwarp();
     return best;
 }
 
-template <int K>
+template <int K, bool FIND>
 __device__ __forceinline__ uint32_t sw16_tile_any(bool first, const int8_t *pptr, int Lp, const uint8_t *pa_t, const uint8_t *pb_t,
                                                   int tla, int tlb, int ncols, int A, uint32_t neg_ge2, uint32_t neg_go2,
-                                                  const uint2 *bnd_rd, uint2 *bnd_wr, bool write_bnd, uint32_t best) {
-    if (first) return sw16_tile<K, true>(pptr, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, write_bnd, best);
-    return sw16_tile<K, false>(pptr, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, write_bnd, best);
+                                                  const uint2 *bnd_rd, uint2 *bnd_wr, bool write_bnd, uint32_t best,
+                                                  uint32_t target = 0, int row_base = 0, uint32_t *key_lo = nullptr,
+                                                  uint32_t *key_hi = nullptr) {
+    if (first) return sw16_tile<K, true, FIND>(pptr, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, write_bnd, best,
+                                               target, row_base, key_lo, key_hi);
+    return sw16_tile<K, false, FIND>(pptr, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, write_bnd, best, target,
+                                     row_base, key_lo, key_hi);
 }
 
 // All pairs of one work item.  The query is cut into full 512-row tiles (16 rows per lane) plus one last tile whose
 // rows-per-lane flavour (4/8/12/16, item.pad_) is the smallest that covers the remainder.
-template <bool SMEM>
+template <bool SMEM, bool FIND>
 __device__ __forceinline__ void sw16_item(const int8_t *prof_base, const QueryDesc &q, const WorkItem &item,
                                           const PairDesc *__restrict__ pairs, const uint8_t *__restrict__ db,
                                           const uint64_t *__restrict__ off, const int32_t *__restrict__ len, int A, int go,
@@ -686,39 +727,55 @@ __device__ __forceinline__ void sw16_item(const int8_t *prof_base, const QueryDe
         p = __shfl_sync(0xffffffffu, p, 0);
         if (p >= item.p1) break;
         const bool has_b = p + 1 < item.p1;
-        const uint32_t ta = pairs[p].target, tb = has_b ? pairs[p + 1].target : ta;
+        const PairDesc pda = pairs[p], pdb = has_b ? pairs[p + 1] : pairs[p];
+        const uint32_t ta = pda.target, tb = pdb.target;
         const int tla = len[ta], tlb = has_b ? len[tb] : 0;
         const uint8_t *pa_t = db + off[ta], *pb_t = db + off[tb];
-        const int ncols = max(tla, tlb);
+        int ncols = max(tla, tlb);
         uint32_t best = 0;
-        for (int tile = 0; tile < n_full; tile++) {
+        uint32_t target = 0, key_lo = 0xffffffffu, key_hi = 0xffffffffu, gkey_lo = 0xffffffffu, gkey_hi = 0xffffffffu;
+        if (FIND) target = ((uint32_t) pda.score & 0xffffu) | ((has_b ? (uint32_t) pdb.score & 0xffffu : 0xffffu) << 16);
+        for (int tile = 0; tile <= n_full; tile++) {
             const uint2 *bnd_rd = (tile & 1) ? bnd0 : bnd1;
             uint2 *bnd_wr = (tile & 1) ? bnd1 : bnd0;
-            best = sw16_tile_any<16>(tile == 0, prof_base + tile * 512 + lane * 16, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2,
-                                     neg_go2, bnd_rd, bnd_wr, true, best);
-        }
-        {
-            const uint2 *bnd_rd = (n_full & 1) ? bnd0 : bnd1;
-            uint2 *bnd_wr = (n_full & 1) ? bnd1 : bnd0;
-            const int8_t *pl = prof_base + n_full * 512 + lane * k_last;
-            switch (k_last) {
-                case 4: best = sw16_tile_any<4>(n_full == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, false, best); break;
-                case 8: best = sw16_tile_any<8>(n_full == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, false, best); break;
-                case 12: best = sw16_tile_any<12>(n_full == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, false, best); break;
-                default: best = sw16_tile_any<16>(n_full == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, false, best); break;
+            const bool last = tile == n_full;
+            const int kk = last ? k_last : 16;
+            const int8_t *pl = prof_base + tile * 512 + lane * kk;
+            switch (kk) {
+                case 4: best = sw16_tile_any<4, FIND>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi); break;
+                case 8: best = sw16_tile_any<8, FIND>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi); break;
+                case 12: best = sw16_tile_any<12, FIND>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi); break;
+                default: best = sw16_tile_any<16, FIND>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi); break;
+            }
+            if (FIND) {   // earliest (column, row) so far per half; later tiles only need the columns up to it
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    key_lo = min(key_lo, __shfl_xor_sync(0xffffffffu, key_lo, o));
+                    key_hi = min(key_hi, __shfl_xor_sync(0xffffffffu, key_hi, o));
+                }
+                gkey_lo = min(gkey_lo, key_lo); gkey_hi = min(gkey_hi, key_hi);
+                key_lo = 0xffffffffu; key_hi = 0xffffffffu;   // every lane may record again in the next tile
+                const int lim_lo = (target & 0xffffu) == 0xffffu ? 0 : (gkey_lo == 0xffffffffu ? tla : (int) (gkey_lo >> 16) + 1);
+                const int lim_hi = (target >> 16) == 0xffffu ? 0 : (gkey_hi == 0xffffffffu ? tlb : (int) (gkey_hi >> 16) + 1);
+                ncols = min(ncols, max(lim_lo, lim_hi));
             }
         }
+        if (!FIND) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) best = __vmaxs2(best, __shfl_xor_sync(0xffffffffu, best, o));
-        if (lane == 0) {
-            out[p] = (int) (best & 0xffffu);
-            if (has_b) out[p + 1] = (int) (best >> 16);
+            for (int o = 16; o > 0; o >>= 1) best = __vmaxs2(best, __shfl_xor_sync(0xffffffffu, best, o));
+            if (lane == 0) {
+                out[p] = (int) (best & 0xffffu);
+                if (has_b) out[p + 1] = (int) (best >> 16);
+            }
+        } else if (lane == 0) {
+            out[2 * p] = (int) (gkey_lo >> 16); out[2 * p + 1] = (int) (gkey_lo & 0xffffu);
+            if (has_b) { out[2 * (p + 1)] = (int) (gkey_hi >> 16); out[2 * (p + 1) + 1] = (int) (gkey_hi & 0xffffu); }
         }
     }
 }
 
 // One launch covers every query length: items carry the rows-per-lane flavour (4/8/12/16) chosen for their query.
-template <bool SMEM, int WARPS>
+template <bool SMEM, int WARPS, bool FIND>
 __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS)
 sw16_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd, const WorkItem *__restrict__ items,
             const PairDesc *__restrict__ pairs, const uint8_t *__restrict__ db, const uint64_t *__restrict__ off,
@@ -760,7 +817,7 @@ sw16_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd,
             __syncthreads();
         }
         const int8_t *pb = SMEM ? (const int8_t *) smem_prof : gprof;
-        sw16_item<SMEM>(pb, q, item, pairs, db, off, len, A, go, ge, bnd0, bnd1, &next_pair, out);
+        sw16_item<SMEM, FIND>(pb, q, item, pairs, db, off, len, A, go, ge, bnd0, bnd1, &next_pair, out);
     }
 }
 
@@ -1227,7 +1284,24 @@ void plan_pairs(const b200_ctx *ctx, const b200_query *queries, const b200_pair 
             Key e; e.k = ((uint64_t) pairs[i].query << 32) | (uint64_t) (0xffffu - (uint32_t) hl[pairs[i].target]); e.i = (uint32_t) i;
             keys.push_back(e);
         }
-    std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) { return a.k != b.k ? a.k < b.k : a.i < b.i; });
+    // stable LSD radix sort on the 48 significant key bits (16 length bits, then the query index), 16 bits per pass;
+    // stability keeps ties in caller order.  ~10x faster than a comparison sort at 10^5..10^6 pairs.
+    {
+        uint32_t maxq = 0;
+        for (const Key &e : keys) maxq = std::max(maxq, (uint32_t) (e.k >> 32));
+        std::vector<Key> tmp(keys.size());
+        std::vector<uint32_t> hist(65536 + 1);
+        const int shifts[3] = {0, 32, 48};
+        const int npass = maxq > 0xffffu ? 3 : (maxq > 0 ? 2 : 1);
+        for (int ps = 0; ps < npass; ps++) {
+            const int sh = shifts[ps];
+            std::fill(hist.begin(), hist.end(), 0u);
+            for (const Key &e : keys) hist[((e.k >> sh) & 0xffffu) + 1]++;
+            for (size_t b2 = 1; b2 < hist.size(); b2++) hist[b2] += hist[b2 - 1];
+            for (const Key &e : keys) tmp[hist[(e.k >> sh) & 0xffffu]++] = e;
+            keys.swap(tmp);
+        }
+    }
     plan.perm.resize(keys.size());
     for (size_t k = 0; k < keys.size(); k++) plan.perm[k] = keys[k].i;
     plan.items.clear();
@@ -1357,6 +1431,60 @@ inline void report_end(const int4 &r, int bias, b200_sw_end &o) {
 
 }  // namespace
 
+namespace {
+int run_sw16_pass(b200_ctx *ctx, const std::vector<QueryDesc> &h_qd, const b200_query *queries, const b200_pair *pairs, uint64_t n,
+                  const uint8_t *mask, const int32_t *scores, int go, int ge, std::vector<int32_t> &res);
+}
+
+// alignScoreEndPos for a batch: packed score kernel on every pair that is safe in int16, packed FIND pass for the end
+// positions of those with a positive score, int32 kernel (score + end in one pass) for the rest.
+static int sw_score_endpos_locked(b200_ctx *ctx, const std::vector<QueryDesc> &h_qd, const b200_query *queries, const b200_pair *pairs,
+                                  uint64_t n, int go, int ge, b200_sw_end *out) {
+    const int A = ctx->alphabet;
+    const int nq = (int) h_qd.size();
+    std::vector<int> smax(nq, 1);
+    for (int i = 0; i < nq; i++) {
+        int m = 1;
+        const int8_t *pr = queries[i].profile;
+        for (size_t k = 0; k < (size_t) A * queries[i].qlen; k++) m = std::max(m, (int) pr[k]);
+        smax[i] = m;
+    }
+    std::vector<uint8_t> packed(n), rest(n);
+    bool any_rest = false, any_packed = false;
+    for (uint64_t i = 0; i < n; i++) {
+        const int qi = (int) pairs[i].query;
+        const int tl = ctx->h_len[pairs[i].target];
+        const bool ok = go >= ge && (int64_t) std::min(queries[qi].qlen, tl) * smax[qi] < 32000;
+        packed[i] = ok ? 1 : 0; rest[i] = ok ? 0 : 1;
+        any_rest |= !ok; any_packed |= ok;
+    }
+    std::vector<int4> res4(n, make_int4(0, -1, -1, 0));
+    if (any_packed) {
+        std::vector<int32_t> score(n, 0), pos(2 * n, -1);
+        int rc = run_sw16_pass(ctx, h_qd, queries, pairs, n, packed.data(), nullptr, go, ge, score);
+        if (rc != B200_OK) return rc;
+        std::vector<uint8_t> need(n);
+        bool any_need = false;
+        for (uint64_t i = 0; i < n; i++) { need[i] = (packed[i] && score[i] > 0) ? 1 : 0; any_need |= need[i] != 0; }
+        if (any_need) {
+            rc = run_sw16_pass(ctx, h_qd, queries, pairs, n, need.data(), score.data(), go, ge, pos);
+            if (rc != B200_OK) return rc;
+        }
+        for (uint64_t i = 0; i < n; i++)
+            if (packed[i] && score[i] > 0) res4[i] = make_int4(score[i], pos[2 * i], pos[2 * i + 1], 0);
+    }
+    if (any_rest) {
+        SwPlan plan;
+        plan_pairs(ctx, queries, pairs, n, rest.data(), plan);
+        std::vector<int4> res;
+        int rc = run_sw_pass<1>(ctx, h_qd, pairs, plan, nullptr, go, ge, res);
+        if (rc != B200_OK) return rc;
+        for (uint32_t s = 0; s < plan.perm.size(); s++) res4[plan.perm[s]] = res[s];
+    }
+    for (uint64_t i = 0; i < n; i++) report_end(res4[i], queries[pairs[i].query].bias, out[i]);
+    return B200_OK;
+}
+
 int b200_sw_score_endpos(b200_ctx *ctx, const b200_query *queries, int nq, const b200_pair *pairs, uint64_t n, int go,
                          int ge, b200_sw_end *out) {
     if (ctx == nullptr) return B200_ERR_ARG;
@@ -1369,16 +1497,7 @@ int b200_sw_score_endpos(b200_ctx *ctx, const b200_query *queries, int nq, const
     std::vector<QueryDesc> h_qd;
     rc = stage_queries(ctx, queries, nq, true, h_qd);
     if (rc != B200_OK) return rc;
-    SwPlan plan;
-    plan_pairs(ctx, queries, pairs, n, nullptr, plan);
-    std::vector<int4> res;
-    rc = run_sw_pass<1>(ctx, h_qd, pairs, plan, nullptr, go, ge, res);
-    if (rc != B200_OK) return rc;
-    for (uint32_t s = 0; s < plan.perm.size(); s++) {
-        const uint32_t i = plan.perm[s];
-        report_end(res[s], queries[pairs[i].query].bias, out[i]);
-    }
-    return B200_OK;
+    return sw_score_endpos_locked(ctx, h_qd, queries, pairs, n, go, ge, out);
 }
 
 static int sw_startpos_locked(b200_ctx *ctx, const b200_query *queries, const std::vector<QueryDesc> &h_qd, const b200_pair *pairs, uint64_t n, int go,
@@ -1435,16 +1554,9 @@ int b200_sw_align(b200_ctx *ctx, const b200_query *queries, int nq, const b200_p
     std::vector<QueryDesc> h_qd;
     rc = stage_queries(ctx, queries, nq, true, h_qd);
     if (rc != B200_OK) return rc;
-    SwPlan plan;
-    plan_pairs(ctx, queries, pairs, n, nullptr, plan);
-    std::vector<int4> res;
-    rc = run_sw_pass<1>(ctx, h_qd, pairs, plan, nullptr, go, ge, res);
-    if (rc != B200_OK) return rc;
     std::vector<b200_sw_end> ends(n);
-    for (uint32_t s = 0; s < plan.perm.size(); s++) {
-        const uint32_t i = plan.perm[s];
-        report_end(res[s], queries[pairs[i].query].bias, ends[i]);
-    }
+    rc = sw_score_endpos_locked(ctx, h_qd, queries, pairs, n, go, ge, ends.data());
+    if (rc != B200_OK) return rc;
     return sw_startpos_locked(ctx, queries, h_qd, pairs, n, go, ge, ends.data(), gate, out);
 }
 
@@ -1510,22 +1622,22 @@ int b200_sw_job_create(b200_ctx *ctx, const b200_query *queries, int nq, const b
 // ---- score-only batch (packed int16x2 fast path + int32 fallback) ---------------------------------------------
 namespace {
 
-template <int WARPS>
+template <int WARPS, bool FIND>
 int launch_sw16_w(b200_ctx *ctx, const QueryDesc *d_qd, const int8_t *d_pad, size_t smem, int smem_profile, const WorkItem *d_items,
                   uint32_t n_items, const PairDesc *d_pairs, int go, int ge, uint2 *d_bnd, int bnd_stride, int32_t *d_out) {
     int per_sm = 0;
     if (smem_profile) {
-        CU_TRY(ctx, cudaFuncSetAttribute(sw16_kernel<true, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw16_kernel<true, WARPS>, WARPS * 32, smem) != cudaSuccess) per_sm = 1;
-    } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw16_kernel<false, WARPS>, WARPS * 32, 0) != cudaSuccess) per_sm = 1;
+        CU_TRY(ctx, cudaFuncSetAttribute(sw16_kernel<true, WARPS, FIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw16_kernel<true, WARPS, FIND>, WARPS * 32, smem) != cudaSuccess) per_sm = 1;
+    } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw16_kernel<false, WARPS, FIND>, WARPS * 32, 0) != cudaSuccess) per_sm = 1;
     per_sm = std::max(1, per_sm);
     const unsigned grid = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) ctx->sm_count * per_sm, n_items));
     if (smem_profile)
-        sw16_kernel<true, WARPS><<<grid, WARPS * 32, smem, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
+        sw16_kernel<true, WARPS, FIND><<<grid, WARPS * 32, smem, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
                                                                          ctx->d_len, ctx->alphabet, go, ge, d_bnd, bnd_stride, n_items,
                                                                          ctx->counter.as<unsigned>(), d_out);
     else
-        sw16_kernel<false, WARPS><<<grid, WARPS * 32, 0, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
+        sw16_kernel<false, WARPS, FIND><<<grid, WARPS * 32, 0, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
                                                                        ctx->d_len, ctx->alphabet, go, ge, d_bnd, bnd_stride, n_items,
                                                                        ctx->counter.as<unsigned>(), d_out);
     ctx->launches++;
@@ -1543,15 +1655,62 @@ int sw16_warps() {  // CTA width of the packed kernel (pairs per item = 2 x warp
 }
 
 int launch_sw16(b200_ctx *ctx, const QueryDesc *d_qd, const int8_t *d_pad, int max_Lp, const WorkItem *d_items, uint32_t n_items,
-                const PairDesc *d_pairs, int go, int ge, uint2 *d_bnd, int bnd_stride, int32_t *d_out) {
+                const PairDesc *d_pairs, int go, int ge, uint2 *d_bnd, int bnd_stride, int32_t *d_out, bool find = false) {
     size_t smem = (size_t) (ctx->alphabet + 1) * max_Lp;
     int smem_profile = 1;
     if (smem > (size_t) ctx->max_smem_optin - 1024) { smem = 0; smem_profile = 0; }
     CU_TRY(ctx, ctx->counter.reserve(sizeof(unsigned)));
     CU_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(unsigned), ctx->stream));
+    if (find) return launch_sw16_w<8, true>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out);
     if (sw16_warps() == 4)
-        return launch_sw16_w<4>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out);
-    return launch_sw16_w<8>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out);
+        return launch_sw16_w<4, false>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out);
+    return launch_sw16_w<8, false>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out);
+}
+
+}  // namespace
+
+
+namespace {
+
+// packed (int16x2) kernel over the pairs selected by `mask`: score mode (scores == nullptr; res[i] = score) or FIND mode
+// (scores[i] = known score > 0; res[2i], res[2i+1] = end column, end row).  Results land at the caller's pair index.
+int run_sw16_pass(b200_ctx *ctx, const std::vector<QueryDesc> &h_qd, const b200_query *queries, const b200_pair *pairs, uint64_t n,
+                  const uint8_t *mask, const int32_t *scores, int go, int ge, std::vector<int32_t> &res) {
+    const bool find = scores != nullptr;
+    SwPlan plan;
+    plan_pairs(ctx, queries, pairs, n, mask, plan, 2u * (uint32_t) (find ? 8 : sw16_warps()));
+    const uint32_t m = (uint32_t) plan.perm.size();
+    if (m == 0) return B200_OK;
+    std::vector<PairDesc> h_pd(m);
+    int max_cols = 1, max_Lp = 0;
+    bool multi = false;
+    for (uint32_t s = 0; s < m; s++) {
+        const uint32_t i = plan.perm[s];
+        h_pd[s].target = pairs[i].target; h_pd[s].qend = 0; h_pd[s].dbend = 0; h_pd[s].score = find ? scores[i] : 0;
+        max_cols = std::max(max_cols, ctx->h_len[pairs[i].target]);
+        max_Lp = std::max(max_Lp, h_qd[pairs[i].query].Lp);
+        if (h_qd[pairs[i].query].qlen > 512) multi = true;
+    }
+    const uint32_t n_items = (uint32_t) plan.items.size();
+    const int bnd_stride = multi ? (int) round_up((uint64_t) max_cols, 32) + 32 : 32;
+    CU_TRY(ctx, ctx->pairs.reserve(sizeof(PairDesc) * m));
+    CU_TRY(ctx, ctx->items.reserve(sizeof(WorkItem) * n_items));
+    CU_TRY(ctx, ctx->out4.reserve(sizeof(int32_t) * 2 * (size_t) m));
+    CU_TRY(ctx, ctx->bnd.reserve(sizeof(int2) * 2 * (size_t) bnd_stride * std::min<uint64_t>(n_items, sw_max_grid(ctx)) * 8));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->pairs.p, h_pd.data(), sizeof(PairDesc) * m, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->items.p, plan.items.data(), sizeof(WorkItem) * n_items, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = launch_sw16(ctx, ctx->qdesc.as<QueryDesc>(), ctx->pad.as<int8_t>(), max_Lp, ctx->items.as<WorkItem>(), n_items,
+                         ctx->pairs.as<PairDesc>(), go, ge, ctx->bnd.as<uint2>(), bnd_stride, ctx->out4.as<int32_t>(), find);
+    if (rc != B200_OK) return rc;
+    std::vector<int32_t> h((size_t) m * (find ? 2 : 1));
+    CU_TRY(ctx, cudaMemcpyAsync(h.data(), ctx->out4.p, sizeof(int32_t) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint32_t s = 0; s < m; s++) {
+        const uint32_t i = plan.perm[s];
+        if (find) { res[2 * (size_t) i] = h[2 * (size_t) s]; res[2 * (size_t) i + 1] = h[2 * (size_t) s + 1]; }
+        else res[i] = h[s];
+    }
+    return B200_OK;
 }
 
 }  // namespace
@@ -1678,14 +1837,47 @@ int b200_sw_score_job_fetch(b200_job *job, int32_t *scores) {
 
 int b200_sw_score(b200_ctx *ctx, const b200_query *queries, int nq, const b200_pair *pairs, uint64_t n, int go, int ge,
                   int32_t *scores) {
-    if (n == 0) return (ctx == nullptr) ? B200_ERR_ARG : B200_OK;
-    b200_job *job = nullptr;
-    int rc = b200_sw_score_job_create(ctx, queries, nq, pairs, n, go, ge, &job);
+    if (ctx == nullptr) return B200_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_pairs(ctx, queries, nq, pairs, n, go, ge);
     if (rc != B200_OK) return rc;
-    rc = b200_job_run(job);
-    if (rc == B200_OK) rc = b200_sw_score_job_fetch(job, scores);
-    b200_job_destroy(job);
-    return rc;
+    if (n == 0) return B200_OK;
+    if (scores == nullptr) return set_err(ctx, B200_ERR_ARG, "sw: scores is NULL");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<QueryDesc> h_qd;
+    rc = stage_queries(ctx, queries, nq, true, h_qd);
+    if (rc != B200_OK) return rc;
+    const int A = ctx->alphabet;
+    std::vector<int> smax(nq, 1);
+    for (int i = 0; i < nq; i++) {
+        int m = 1;
+        const int8_t *pr = queries[i].profile;
+        for (size_t k = 0; k < (size_t) A * queries[i].qlen; k++) m = std::max(m, (int) pr[k]);
+        smax[i] = m;
+    }
+    std::vector<uint8_t> packed(n), rest(n);
+    bool any_rest = false, any_packed = false;
+    for (uint64_t i = 0; i < n; i++) {
+        const int qi = (int) pairs[i].query;
+        const bool ok = go >= ge && (int64_t) std::min(queries[qi].qlen, ctx->h_len[pairs[i].target]) * smax[qi] < 32000;
+        packed[i] = ok ? 1 : 0; rest[i] = ok ? 0 : 1;
+        any_rest |= !ok; any_packed |= ok;
+    }
+    std::vector<int32_t> sc(n, 0);
+    if (any_packed) {
+        rc = run_sw16_pass(ctx, h_qd, queries, pairs, n, any_rest ? packed.data() : nullptr, nullptr, go, ge, sc);
+        if (rc != B200_OK) return rc;
+    }
+    if (any_rest) {
+        SwPlan plan;
+        plan_pairs(ctx, queries, pairs, n, rest.data(), plan);
+        std::vector<int4> res;
+        rc = run_sw_pass<1>(ctx, h_qd, pairs, plan, nullptr, go, ge, res);
+        if (rc != B200_OK) return rc;
+        for (uint32_t s2 = 0; s2 < plan.perm.size(); s2++) sc[plan.perm[s2]] = std::min(res[s2].x, 32767);
+    }
+    memcpy(scores, sc.data(), sizeof(int32_t) * n);
+    return B200_OK;
 }
 
 int b200_job_run(b200_job *job) {

@@ -2,3 +2,5 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -25 gpurun_out/pytest_gpu.log
+python scripts/sw_perf.py > gpurun_out/sw_perf.log 2>&1
+cat gpurun_out/sw_perf.log

@@ -37,11 +37,18 @@ def main():
         ctx.sw_score(profs, spairs)
         dt = time.perf_counter() - t0
     print("e2e sw_score: %.1f ms  %.1f GCUPS" % (dt * 1e3, cells / 1e9 / dt))
+    for rep in range(3):
+        t0 = time.perf_counter()
+        ends = ctx.sw_score_endpos(profs, spairs)
+        dt = time.perf_counter() - t0
+    print("e2e sw_score_endpos (packed score + packed FIND): %.1f ms  %.1f GCUPS" % (dt * 1e3, cells / 1e9 / dt))
     sjob = ctx.sw_job(profs, spairs)
     sjob.run(); ctx.sync()
     ctx.event_record(2); sjob.run(); ctx.event_record(3)
     ms2 = ctx.event_elapsed_ms(2, 3)
     print("sw32 score+end: %.3f ms  %.1f GCUPS" % (ms2, cells / 1e9 / (ms2 / 1e3)))
+    e32 = sjob.fetch()
+    assert np.array_equal(e32, ends), "packed FIND path differs from the int32 kernel"
     sjob.close()
     ctx.close()
 

@@ -51,8 +51,8 @@ def test_operator_mirror_matches_oracle(tmp_path, built_lib, oracle, blosum):
     for k in np.nonzero(passed)[0]:   # alignment mode 2: identities + backtrace length from the device CIGAR
         if exp[k, 4] == -1:
             continue
-        bt, ids = oracle.backtrace(q, cb, res[int(to[k]):int(to[k + 1])], exp[k])
-        assert full[k, 6] == ids and full[k, 7] == len(bt), k
+        bt, n_ident = oracle.backtrace(q, cb, res[int(to[k]):int(to[k + 1])], exp[k])
+        assert full[k, 6] == n_ident and full[k, 7] == len(bt), k
     rest = out[300 * 8:]
     n_scan = rest[0]
     scan = rest[1:101].reshape(50, 2)
