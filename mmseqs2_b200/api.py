@@ -335,10 +335,11 @@ class Context:
         ta = np.zeros(len(tasks), NUCL_TASK_DTYPE)
         tarr = np.asarray(tasks, np.int64).reshape(-1, 3)
         ta["query"], ta["target"], ta["diagonal"] = tarr[:, 0], tarr[:, 1], tarr[:, 2] & 0xffff
-        slots = np.array([2 * len(queries[int(q)]) + 72 for q in tarr[:, 0]], np.uint64)
+        qlens = np.array([len(q) for q in queries], np.int64)
+        slots = (2 * qlens[tarr[:, 0]] + 72).astype(np.uint64)
         coff = np.zeros(len(ta) + 1, np.uint64)
         coff[1:] = np.cumsum(slots)
-        cig = np.zeros(int(coff[-1]) + 1, np.uint32)
+        cig = np.empty(int(coff[-1]) + 1, np.uint32)   # only out[i].n_cigar entries of each slot are written
         out = np.zeros(len(ta), NUCL_ALN_DTYPE)
         self._check(self.lib.b200_nucl_align(self.h, _p(qres), _p(qoff), ctypes.c_uint32(len(queries)), _p(ta), _u64(len(ta)), go, ge,
                                              zdrop, _p(out), _p(cig), _p(coff)))

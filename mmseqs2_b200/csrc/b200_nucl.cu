@@ -275,8 +275,9 @@ __global__ void __launch_bounds__(NUCL_WARPS * 32)
 nucl_align_kernel(const NuclTask *__restrict__ tasks, unsigned n_tasks, const uint8_t *__restrict__ qres,
                   const uint64_t *__restrict__ qoff, const uint8_t *__restrict__ db, const uint64_t *__restrict__ off,
                   const int32_t *__restrict__ len, int gapo, int gape, int zdrop, int w, uint8_t *__restrict__ scratch,
-                  size_t scratch_stride, size_t mem_bytes, size_t h_bytes, size_t p_bytes, unsigned *__restrict__ counter,
-                  int32_t *__restrict__ out, uint32_t *__restrict__ cigars, int cigar_cap_slack) {
+                  size_t scratch_stride, size_t mem_bytes, size_t h_bytes, size_t p_bytes, size_t pm_bytes, unsigned *__restrict__ counter,
+                  int32_t *__restrict__ out, uint32_t *__restrict__ pool, unsigned long long *__restrict__ pool_used,
+                  int cigar_cap_slack) {
     __shared__ int8_t smat[25];
     if (threadIdx.x < 25) {  // nucleotide.out at bit factor 1: +2 / -3, X column/row -3 (NucleotideMatrix), ksw treats X as 0
         const int a = threadIdx.x / 5, b = threadIdx.x % 5;
@@ -288,7 +289,8 @@ nucl_align_kernel(const NuclTask *__restrict__ tasks, unsigned n_tasks, const ui
     uint8_t *mem = scratch + (size_t) warp_global * scratch_stride;
     const size_t mh_cap = mem_bytes + h_bytes;   // per-warp capacity of (byte arrays + H)
     int2 *poff = reinterpret_cast<int2 *>(mem + mem_bytes + h_bytes);
-    uint8_t *pmat = mem + mem_bytes + h_bytes + p_bytes;  // p_bytes here = size of the poff area; the rest is the matrix
+    uint8_t *pmat = mem + mem_bytes + h_bytes + p_bytes;  // p_bytes = size of the poff area, pm_bytes = direction matrix
+    uint32_t *cigar = reinterpret_cast<uint32_t *>(pmat + pm_bytes);   // per-warp CIGAR staging; finished ops go to the pool
     const int8_t sc_mch = 2, sc_mis = -3;
 
     while (true) {
@@ -301,7 +303,6 @@ nucl_align_kernel(const NuclTask *__restrict__ tasks, unsigned n_tasks, const ui
         const int qL = (int) (qoff[task.query + 1] - qoff[task.query]);
         const uint8_t *t = db + off[task.target];
         const int tL = len[task.target];
-        uint32_t *cigar = cigars + task.cigar_off;
         const int cigar_cap = 2 * qL + cigar_cap_slack;
         int32_t *o = out + (size_t) ti * 8;
         // ---- ungapped seed on the prefilter diagonal (two wrap candidates), lane 0
@@ -328,8 +329,9 @@ nucl_align_kernel(const NuclTask *__restrict__ tasks, unsigned n_tasks, const ui
 #pragma unroll
             for (int s2 = 16; s2 > 0; s2 >>= 1) ids += __shfl_xor_sync(0xffffffffu, ids, s2);
             if (lane == 0) {
-                o[0] = best_score; o[1] = qUs; o[2] = qUe; o[3] = dUs; o[4] = dUe; o[5] = ids; o[6] = 1; o[7] = 0;
-                cigar[0] = (uint32_t) qL << 4;
+                const unsigned long long po = atomicAdd(pool_used, 1ull);
+                pool[po] = (uint32_t) qL << 4;
+                o[0] = best_score; o[1] = qUs; o[2] = qUe; o[3] = dUs; o[4] = dUe; o[5] = ids; o[6] = 1; o[7] = (int32_t) (uint32_t) po;
             }
             continue;
         }
@@ -360,8 +362,10 @@ nucl_align_kernel(const NuclTask *__restrict__ tasks, unsigned n_tasks, const ui
                 else if (op == 1) qp += ln;
                 else tp += ln;
             }
+            const unsigned long long po = atomicAdd(pool_used, (unsigned long long) n);
+            for (int c = 0; c < n; c++) pool[po + c] = cigar[c];
             o[0] = ezA.max; o[1] = qStartPos; o[2] = qStartPos + ezA.max_q; o[3] = tStartPos; o[4] = tStartPos + ezA.max_t;
-            o[5] = ids; o[6] = ezA.n_cigar; o[7] = reversed ? 1 : 0;
+            o[5] = ids; o[6] = n; o[7] = (int32_t) (uint32_t) po;
         }
         __syncwarp();
     }
@@ -408,7 +412,8 @@ int b200_nucl_align(b200_ctx *ctx, const uint8_t *query_residues, const uint64_t
     const size_t poff_bytes = round_up(rows * sizeof(int2), 16);
     const size_t n_col = ((std::min<size_t>(std::min(max_q, max_t), w + 1) + 15) / 16 + 1) * 16;
     const size_t pm_bytes = round_up(rows * n_col + 64, 16);
-    const size_t stride = mem_bytes + h_bytes + poff_bytes + pm_bytes;
+    const size_t cig_stage_bytes = round_up(((size_t) 2 * max_q + w + 8) * sizeof(uint32_t), 16);
+    const size_t stride = mem_bytes + h_bytes + poff_bytes + pm_bytes + cig_stage_bytes;
     const size_t smem_need = round_up(mem_bytes + h_bytes, 16) * NUCL_WARPS;
     const bool use_smem = smem_need <= 96 * 1024;
     int per_sm = 0;
@@ -418,14 +423,18 @@ int b200_nucl_align(b200_ctx *ctx, const uint8_t *query_residues, const uint64_t
     } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nucl_align_kernel<false>, NUCL_WARPS * 32, 0) != cudaSuccess) per_sm = 1;
     per_sm = std::max(1, per_sm);
     const unsigned grid = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) ctx->sm_count * per_sm, (n + NUCL_WARPS - 1) / NUCL_WARPS));
-    const uint64_t cig_total = cigar_offsets[n];
-    DevBuf d_tasks, d_q, d_qoff, d_scratch, d_out, d_cig;
+    uint64_t pool_cap = 0;   // worst case: every alignment fills its slot; what comes back over PCIe is only what was used
+    for (uint64_t i = 0; i < n; i++) pool_cap += 2 * (query_offsets[tasks[i].query + 1] - query_offsets[tasks[i].query]) + w + 8;
+    if (pool_cap >= 0xffffffffull) return b200_set_err(ctx, B200_ERR_RANGE, "b200_nucl_align: CIGAR pool too large, split the batch");
+    DevBuf d_tasks, d_q, d_qoff, d_scratch, d_out, d_cig, d_used;
     cudaError_t e = d_tasks.reserve(sizeof(NuclTask) * n);
     if (e == cudaSuccess) e = d_q.reserve(q_total + 16);
     if (e == cudaSuccess) e = d_qoff.reserve(sizeof(uint64_t) * ((size_t) n_queries + 1));
     if (e == cudaSuccess) e = d_scratch.reserve(stride * (size_t) grid * NUCL_WARPS);
     if (e == cudaSuccess) e = d_out.reserve(sizeof(int32_t) * 8 * n);
-    if (e == cudaSuccess) e = d_cig.reserve(sizeof(uint32_t) * cig_total + 16);
+    if (e == cudaSuccess) e = d_cig.reserve(sizeof(uint32_t) * pool_cap + 16);
+    if (e == cudaSuccess) e = d_used.reserve(sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_used.p, 0, sizeof(unsigned long long), ctx->stream);
     if (e == cudaSuccess) e = ctx->counter.reserve(sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemsetAsync(ctx->counter.p, 0, sizeof(unsigned), ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_tasks.p, h_tasks.data(), sizeof(NuclTask) * n, cudaMemcpyHostToDevice, ctx->stream);
@@ -435,26 +444,31 @@ int b200_nucl_align(b200_ctx *ctx, const uint8_t *query_residues, const uint64_t
         if (use_smem)
             nucl_align_kernel<true><<<grid, NUCL_WARPS * 32, smem_need, ctx->stream>>>(
                 d_tasks.as<NuclTask>(), (unsigned) n, d_q.as<uint8_t>(), d_qoff.as<uint64_t>(), ctx->d_res, ctx->d_off, ctx->d_len, gap_open,
-                gap_extend, zdrop, w, d_scratch.as<uint8_t>(), stride, mem_bytes, h_bytes, poff_bytes, ctx->counter.as<unsigned>(),
-                d_out.as<int32_t>(), d_cig.as<uint32_t>(), w + 8);
+                gap_extend, zdrop, w, d_scratch.as<uint8_t>(), stride, mem_bytes, h_bytes, poff_bytes, pm_bytes, ctx->counter.as<unsigned>(),
+                d_out.as<int32_t>(), d_cig.as<uint32_t>(), d_used.as<unsigned long long>(), w + 8);
         else
             nucl_align_kernel<false><<<grid, NUCL_WARPS * 32, 0, ctx->stream>>>(
                 d_tasks.as<NuclTask>(), (unsigned) n, d_q.as<uint8_t>(), d_qoff.as<uint64_t>(), ctx->d_res, ctx->d_off, ctx->d_len, gap_open,
-                gap_extend, zdrop, w, d_scratch.as<uint8_t>(), stride, mem_bytes, h_bytes, poff_bytes, ctx->counter.as<unsigned>(),
-                d_out.as<int32_t>(), d_cig.as<uint32_t>(), w + 8);
+                gap_extend, zdrop, w, d_scratch.as<uint8_t>(), stride, mem_bytes, h_bytes, poff_bytes, pm_bytes, ctx->counter.as<unsigned>(),
+                d_out.as<int32_t>(), d_cig.as<uint32_t>(), d_used.as<unsigned long long>(), w + 8);
         ctx->launches++;
         e = cudaGetLastError();
     }
     std::vector<int32_t> h_out(8 * n);
+    unsigned long long used = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_out.data(), d_out.p, sizeof(int32_t) * 8 * n, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(cigars, d_cig.p, sizeof(uint32_t) * cig_total, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&used, d_used.p, sizeof(used), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    d_tasks.release(); d_q.release(); d_qoff.release(); d_scratch.release(); d_out.release(); d_cig.release();
+    std::vector<uint32_t> h_pool((size_t) used + 1);
+    if (e == cudaSuccess && used > 0) e = cudaMemcpyAsync(h_pool.data(), d_cig.p, sizeof(uint32_t) * used, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    d_tasks.release(); d_q.release(); d_qoff.release(); d_scratch.release(); d_out.release(); d_cig.release(); d_used.release();
     if (e != cudaSuccess) { ctx->err = std::string("b200_nucl_align: ") + cudaGetErrorString(e); return B200_ERR_CUDA; }
     for (uint64_t i = 0; i < n; i++) {
         const int32_t *o = h_out.data() + 8 * i;
         out[i].score = o[0]; out[i].qstart = o[1]; out[i].qend = o[2]; out[i].dbstart = o[3]; out[i].dbend = o[4];
         out[i].identical = o[5]; out[i].n_cigar = o[6];
+        if (o[6] > 0) memcpy(cigars + cigar_offsets[i], h_pool.data() + (uint32_t) o[7], sizeof(uint32_t) * (size_t) o[6]);
     }
     return B200_OK;
 }

@@ -244,6 +244,36 @@ def test_properties_at_scale(ctx, submat, blosum):
         assert selfp["qstart"][a] == 0 and selfp["dbstart"][a] == 0
 
 
+def test_shared_context_from_many_host_threads(ctx, golden, golden_db, submat):
+    """the reference keeps one operator object per OpenMP thread; here they share one ctx (internal mutex)"""
+    import threading
+    qs = _queries(golden)[3:9]
+    profs = [submat.ssw_query(q) for q in qs]
+    n = len(golden["toff"]) - 1
+    pairs = np.array([(qi, t) for qi in range(len(qs)) for t in range(0, n, 2)], np.uint32)
+    exp_sc = ctx.sw_score(profs, pairs)
+    exp_hits, exp_n, _ = ctx.ungapped_scan(profs, max_hits=40)
+    errors = []
+
+    def worker(k):
+        try:
+            for _ in range(4):
+                if k % 2:
+                    assert np.array_equal(ctx.sw_score(profs, pairs), exp_sc)
+                else:
+                    h, nh, _ = ctx.ungapped_scan(profs, max_hits=40)
+                    assert np.array_equal(h, exp_hits) and np.array_equal(nh, exp_n)
+        except Exception as e:  # pragma: no cover
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=worker, args=(k,)) for k in range(6)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+
+
 def test_error_paths(ctx, submat, blosum):
     from mmseqs2_b200 import B200Error
     rng = np.random.default_rng(1)
