@@ -72,6 +72,8 @@ uint64_t b200_launch_count(const b200_ctx *ctx);
 int b200_event_record(b200_ctx *ctx, int slot /*0..15*/);
 int b200_event_elapsed_ms(b200_ctx *ctx, int slot_a, int slot_b, float *ms); /* synchronises on slot_b */
 int b200_sync(b200_ctx *ctx);
+/* device time (CUDA events on the ctx stream) of the kernels launched by the last b200_nucl_align / b200_sw_backtrace call */
+float b200_last_kernel_ms(const b200_ctx *ctx);
 
 /* ---- target DB ------------------------------------------------------------------------------- */
 /* residues: numeric codes 0..alphabet-1, sequence i = residues[offsets[i] .. offsets[i+1]).  Copied to HBM. */

@@ -208,6 +208,12 @@ class Context:
     def launches(self):
         return int(self.lib.b200_launch_count(self.h))
 
+    @property
+    def last_kernel_ms(self):
+        self.lib.b200_last_kernel_ms.restype = ctypes.c_float
+        self.lib.b200_last_kernel_ms.argtypes = [_vp]
+        return float(self.lib.b200_last_kernel_ms(self.h))
+
     def sync(self):
         self._check(self.lib.b200_sync(self.h))
 
@@ -329,19 +335,24 @@ class Context:
     def nucl_align(self, queries, tasks, go=5, ge=2, zdrop=40, decode=True):
         """queries: list of uint8 arrays (A,C,T,G,X = 0..4); tasks: iterable of (query, target, diagonal_u16).
         -> (structured results, list of cigar op arrays, list of backtrace strings)"""
-        qres = np.ascontiguousarray(np.concatenate(queries), np.uint8)
-        qoff = np.zeros(len(queries) + 1, np.uint64)
-        qoff[1:] = np.cumsum([len(q) for q in queries])
+        if isinstance(queries, tuple):          # already packed: (residues uint8, offsets uint64[n+1])
+            qres = np.ascontiguousarray(queries[0], np.uint8)
+            qoff = np.ascontiguousarray(queries[1], np.uint64)
+            qlens = np.diff(qoff.astype(np.int64))
+        else:
+            qres = np.ascontiguousarray(np.concatenate(queries), np.uint8)
+            qlens = np.array([len(q) for q in queries], np.int64)
+            qoff = np.zeros(len(qlens) + 1, np.uint64)
+            qoff[1:] = np.cumsum(qlens)
         ta = np.zeros(len(tasks), NUCL_TASK_DTYPE)
         tarr = np.asarray(tasks, np.int64).reshape(-1, 3)
         ta["query"], ta["target"], ta["diagonal"] = tarr[:, 0], tarr[:, 1], tarr[:, 2] & 0xffff
-        qlens = np.array([len(q) for q in queries], np.int64)
         slots = (2 * qlens[tarr[:, 0]] + 72).astype(np.uint64)
         coff = np.zeros(len(ta) + 1, np.uint64)
         coff[1:] = np.cumsum(slots)
         cig = np.empty(int(coff[-1]) + 1, np.uint32)   # only out[i].n_cigar entries of each slot are written
         out = np.zeros(len(ta), NUCL_ALN_DTYPE)
-        self._check(self.lib.b200_nucl_align(self.h, _p(qres), _p(qoff), ctypes.c_uint32(len(queries)), _p(ta), _u64(len(ta)), go, ge,
+        self._check(self.lib.b200_nucl_align(self.h, _p(qres), _p(qoff), ctypes.c_uint32(len(qlens)), _p(ta), _u64(len(ta)), go, ge,
                                              zdrop, _p(out), _p(cig), _p(coff)))
         if not decode:
             return out, (cig, coff), None

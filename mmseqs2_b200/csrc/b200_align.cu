@@ -1017,6 +1017,7 @@ int b200_device_info(const b200_ctx *ctx, int *sm_count, int *cc_major, int *cc_
 }
 
 uint64_t b200_launch_count(const b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+float b200_last_kernel_ms(const b200_ctx *ctx) { return ctx ? ctx->last_kernel_ms : 0.f; }
 
 int b200_event_record(b200_ctx *ctx, int slot) {
     if (ctx == nullptr || slot < 0 || slot >= 16) return B200_ERR_ARG;

@@ -77,6 +77,7 @@ struct b200_ctx {
     std::mutex mu;
     std::string err;
     uint64_t launches = 0;
+    float last_kernel_ms = 0.f;  // device time of the kernels of the last one-shot call that measures it (b200_last_kernel_ms)
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     uint64_t hbm = 0;
     int max_smem_optin = 0;

@@ -440,6 +440,7 @@ int b200_nucl_align(b200_ctx *ctx, const uint8_t *query_residues, const uint64_t
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_tasks.p, h_tasks.data(), sizeof(NuclTask) * n, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_q.p, query_residues, q_total, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_qoff.p, query_offsets, sizeof(uint64_t) * ((size_t) n_queries + 1), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[14], ctx->stream);
     if (e == cudaSuccess) {
         if (use_smem)
             nucl_align_kernel<true><<<grid, NUCL_WARPS * 32, smem_need, ctx->stream>>>(
@@ -453,6 +454,7 @@ int b200_nucl_align(b200_ctx *ctx, const uint8_t *query_residues, const uint64_t
                 d_out.as<int32_t>(), d_cig.as<uint32_t>(), d_used.as<unsigned long long>(), w + 8);
         ctx->launches++;
         e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[15], ctx->stream);
     }
     std::vector<int32_t> h_out(8 * n);
     unsigned long long used = 0;
@@ -462,6 +464,7 @@ int b200_nucl_align(b200_ctx *ctx, const uint8_t *query_residues, const uint64_t
     std::vector<uint32_t> h_pool((size_t) used + 1);
     if (e == cudaSuccess && used > 0) e = cudaMemcpyAsync(h_pool.data(), d_cig.p, sizeof(uint32_t) * used, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev[14], ctx->ev[15]);
     d_tasks.release(); d_q.release(); d_qoff.release(); d_scratch.release(); d_out.release(); d_cig.release(); d_used.release();
     if (e != cudaSuccess) { ctx->err = std::string("b200_nucl_align: ") + cudaGetErrorString(e); return B200_ERR_CUDA; }
     for (uint64_t i = 0; i < n; i++) {
