@@ -177,6 +177,14 @@ class Ref:
         self.lib.ref_get_matrix(1 if nucl else 0, _p(mat), _p(pb), n2a)
         return mat, pb, n2a.raw.decode()
 
+    def evalue(self, go, ge, db_residues, score, qlen):
+        return float(self.lib.ref_evalue(go, ge, ctypes.c_int64(db_residues), ctypes.c_double(score), ctypes.c_double(qlen), None))
+
+    def aa2num(self, nucl=False):
+        t = np.zeros(256, np.uint8)
+        self.lib.ref_aa2num(1 if nucl else 0, _p(t))
+        return t
+
     def comp_bias(self, q, scale=1.0):
         q = np.ascontiguousarray(q, np.uint8)
         out = np.zeros(len(q), np.float32)

@@ -18,6 +18,74 @@ from mmseqs2_b200 import synth  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
+def read_fasta(path, limit):
+    seqs, cur = [], []
+    with open(path) as f:
+        for line in f:
+            if line.startswith(">"):
+                if cur:
+                    seqs.append("".join(cur)); cur = []
+                    if len(seqs) >= limit:
+                        break
+            else:
+                cur.append(line.strip())
+    if cur and len(seqs) < limit:
+        seqs.append("".join(cur))
+    return seqs
+
+
+def make_examples(ref):
+    """tests/golden/examples_v1.npz: real proteins (BASELINE config[0] data: the reference's examples/QUERY.fasta and
+    DB.fasta, first 40 queries x first 600 targets, residues mapped with the reference's aa2num) and the reference's outputs"""
+    a2n = ref.aa2num()
+    qs = [a2n[np.frombuffer(s.encode(), np.uint8)] for s in read_fasta("/root/reference/examples/QUERY.fasta", 40)]
+    pool = [a2n[np.frombuffer(s.encode(), np.uint8)] for s in read_fasta("/root/reference/examples/DB.fasta", 8000)]
+    pd_, po_ = pack_targets(pool)
+    chosen = []
+    for q in qs:                                  # make sure real homologs are in the 600-target mini DB
+        sc = ref.ungapped(q, 1, pd_, po_)
+        top = np.argsort(-sc, kind="stable")[:12]
+        chosen.extend(int(t) for t in top if sc[t] > 15)
+    chosen = sorted(set(chosen))
+    rest = [i for i in range(len(pool)) if i not in set(chosen)]
+    ids600 = sorted(chosen + rest[:max(0, 600 - len(chosen))])[:600] if len(chosen) < 600 else chosen[:600]
+    ts = [pool[i] for i in ids600]
+    td, to = pack_targets(ts)
+    qd, qo = pack_targets(qs)
+    ung = np.stack([ref.ungapped(q, 1, td, to) for q in qs])
+    aln = np.stack([ref.ssw_align(q, 1, td, to, mode=1)[0][:, :6] for q in qs])
+    # end-to-end hit lists the way `search --prefilter-mode 1` produces them on this mini DB:
+    #   ungappedprefilter: score > 15, order (score desc, id asc), top 300          (ungappedprefilter.cpp:450-478)
+    #   align: ssw_align mode 1, accept evalue <= 1e-3, order Matcher::compareHits  (Alignment.cpp:346-405, Matcher.h:161-172)
+    db_res = int(to[-1])
+    tlen = np.diff(to)
+    hit_off, hit_ids, hit_rows, min_score = [0], [], [], []
+    for qi, q in enumerate(qs):
+        sc = ung[qi].astype(np.int64)
+        ids = np.nonzero(sc > 15)[0]
+        ids = ids[np.lexsort((ids, -sc[ids]))][:300]
+        sd, so = pack_targets([ts[i] for i in ids]) if len(ids) else (np.zeros(0, np.uint8), np.zeros(1, np.int64))
+        accepted = []
+        if len(ids):
+            a, ev, _ = ref.ssw_align(q, 1, sd, so, mode=1, eval_thr=1e-3, db_residues=db_res)
+            for k, t in enumerate(ids):
+                if a[k, 4] != -1 and ev[k] <= 1e-3:
+                    accepted.append((ev[k], -int(a[k, 0]), int(tlen[t]), int(t), a[k, :6].copy()))
+        accepted.sort(key=lambda r: r[:4])
+        hit_ids.extend(r[3] for r in accepted)
+        hit_rows.extend(r[4] for r in accepted)
+        hit_off.append(len(hit_ids))
+        ms = 1
+        while ref.evalue(11, 1, db_res, ms, len(q)) > 1e-3:
+            ms += 1
+        min_score.append(ms)
+    np.savez_compressed(os.path.join(HERE, "examples_v1.npz"), qdata=qd, qoff=qo, tdata=td, toff=to, ungapped=ung.astype(np.uint8),
+                        align=aln.astype(np.int32), hit_off=np.array(hit_off, np.int64), hit_ids=np.array(hit_ids, np.int64),
+                        hit_rows=np.array(hit_rows, np.int32).reshape(-1, 6), min_score=np.array(min_score, np.int32))
+    print("search fixture:", len(hit_ids), "accepted hits, min scores", min(min_score), "-", max(min_score))
+    print("examples fixture:", len(qs), "x", len(ts), "max ungapped", int(ung.max()), "word pairs", int(aln[:, :, 5].sum()))
+
+
 def make_nucl(ref):
     """tests/golden/nucl_v1.npz: reads against genome pieces, outputs of the reference's BandedNucleotideAligner::align"""
     rng = np.random.default_rng(5150)
@@ -93,6 +161,7 @@ def main():
         out["q%d_compbias" % qi] = f
     np.savez_compressed(os.path.join(HERE, "hotpath_v1.npz"), **out)
     make_nucl(ref)
+    make_examples(ref)
     print("wrote fixtures:", {k: os.path.getsize(os.path.join(HERE, k)) for k in ("blosum62.npz", "hotpath_v1.npz")})
 
 
