@@ -97,7 +97,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 // that a group's LDS.128 is conflict-free.
 // ------------------------------------------------------------------------------------------------
 template <int G, int K, bool TILED>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (K <= 12 && !TILED) ? 5 : 1)
 ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict__ qd, const uint8_t *__restrict__ db,
                      const uint64_t *__restrict__ off, const int32_t *__restrict__ len,
                      const uint32_t *__restrict__ order, uint32_t n_seq, int A, uint8_t *__restrict__ out, uint32_t n_queries,
