@@ -406,6 +406,28 @@ def main():
             roof["clock_mhz_used"] = clk_mhz
         line["roofline"] = roof
 
+        # ---- secondary: the whole hot path of `search --prefilter-mode 1` for one query batch, host buffers end to end:
+        #      ungapped scan of the DB -> top hits -> gapped score of every hit -> score gate -> end/start positions of survivors
+        if not args.no_secondary and world == 1:
+            try:
+                def search_once(bt):
+                    h, nh, _ = ctx.ungapped_scan(bt, 15, args.max_hits)
+                    prs = np.array([(qi, int(t)) for qi in range(len(bt)) for t in h[qi]["id"][:int(nh[qi])]], np.uint32).reshape(-1, 2)
+                    sc = ctx.sw_score(bt, prs)
+                    gate = (sc >= 60).astype(np.uint8)      # ~ E-value 1e-3 against this DB size (tests/golden: 63-89 on a 600-seq DB)
+                    al = ctx.sw_align(bt, prs, gate=gate)
+                    return len(prs), int(gate.sum()), al
+                search_once(batches[0])
+                t0 = time.perf_counter()
+                n_pairs, n_surv, _ = search_once(batches[1])
+                sdt = time.perf_counter() - t0
+                line.setdefault("secondary", {})["search_pipeline"] = {
+                    "workload": "scan + rescoring of the top-%d hits for %d queries vs the %d-seq DB (host buffers, one batch)" % (args.max_hits, len(batches[1]), args.db_seqs),
+                    "queries_per_s": len(batches[1]) / sdt, "ms": sdt * 1e3, "prefilter_hits": n_pairs, "survivors": n_surv,
+                    "GCUPS_scan_equivalent": cells_per_step[1] / 1e9 / sdt}
+            except Exception as e:  # pragma: no cover
+                line.setdefault("secondary", {})["search_pipeline"] = {"error": repr(e)}
+
         # ---- secondary: gapped SW rescoring (config[2] shape) ------------------------------------------------
         if not args.no_secondary and world == 1:
             try:

@@ -1,8 +1,9 @@
 #!/bin/bash
-# 2-GPU run of the bench through torchrun (NCCL gather of the hit lists), plus the reference arm
+# N-GPU run of the bench through torchrun (NCCL gather of the hit lists)
+N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/gpus.txt
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "exit $?"
-cat gpurun_out/bench_n2.json; tail -5 gpurun_out/bench_n2.err
-timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "exit $?"
-cat gpurun_out/bench_ref.json; tail -3 gpurun_out/bench_ref.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "exit $?"
+cat gpurun_out/bench_n$N.json | cut -c1-400; tail -3 gpurun_out/bench_n$N.err
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --impl reference --gpus $N --steps 2 --warmup 1 > gpurun_out/bench_ref_n$N.json 2> gpurun_out/bench_ref_n$N.err; echo "exit $?"
+cat gpurun_out/bench_ref_n$N.json | cut -c1-300

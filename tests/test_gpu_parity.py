@@ -274,6 +274,37 @@ def test_shared_context_from_many_host_threads(ctx, golden, golden_db, submat):
     assert not errors, errors
 
 
+def test_empty_and_tiny_sequences(ctx, oracle, submat, blosum):
+    """zero-length targets, 1-residue targets/queries, a DB of a single sequence"""
+    rng = np.random.default_rng(3)
+    bg = synth.background(blosum[1])
+    seqs = [np.zeros(0, np.uint8), np.array([5], np.uint8), synth.random_seqs(rng, 1, bg, mean=40, sigma=0, lo=40, hi=40, normal=True)[0],
+            np.zeros(0, np.uint8), np.array([19, 19], np.uint8)]
+    td, to = pack_targets(seqs)
+    ctx.load_db(td, to.astype(np.uint64), 21)
+    qs = [np.array([5], np.uint8), seqs[2][5:30].copy(), np.array([19, 19, 19], np.uint8)]
+    profs = [submat.ssw_query(q) for q in qs]
+    _, _, dense = ctx.ungapped_scan(profs, want_dense=True)
+    pairs = np.array([(qi, t) for qi in range(len(qs)) for t in range(len(seqs))], np.uint32)
+    aln = ctx.sw_align(profs, pairs)
+    sc = ctx.sw_score(profs, pairs)
+    for qi, q in enumerate(qs):
+        cb, bias = oracle.query_cb(q, True)
+        nz = [k for k in range(len(seqs)) if len(seqs[k]) > 0]
+        sd, so = pack_targets([seqs[k] for k in nz])
+        assert np.array_equal(dense[qi][nz].astype(np.int32), oracle.ungapped(q, cb, bias, sd, so))
+        exp = oracle.sw_align(q, cb, bias, sd, so)
+        got = np.stack([aln[f][qi * len(seqs):(qi + 1) * len(seqs)] for f in ("score", "qstart", "qend", "dbstart", "dbend", "word")], 1)
+        assert np.array_equal(got[nz], exp), qi
+        for k in range(len(seqs)):
+            if len(seqs[k]) == 0:   # nothing to align: score 0, "no residue aligned"
+                assert dense[qi][k] == 0 and got[k, 0] == 0 and got[k, 4] == -1 and sc[qi * len(seqs) + k] == 0
+    one = pack_targets([seqs[2]])
+    ctx.load_db(one[0], one[1].astype(np.uint64), 21)
+    h, nh, _ = ctx.ungapped_scan([profs[1]], min_score_excl=0, max_hits=5)
+    assert nh[0] == 1 and h[0]["id"][0] == 0
+
+
 def test_error_paths(ctx, submat, blosum):
     from mmseqs2_b200 import B200Error
     rng = np.random.default_rng(1)
