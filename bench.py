@@ -490,10 +490,10 @@ def main():
                                                        "ops_per_cell": SW32_OPS_PER_CELL}
                 if not args.no_cpu:
                     sec["cpu_baseline"] = cpu_reference_sw(sq, std, sto, spairs, 10.0, os.cpu_count() or 1)
-                line["secondary"] = {"sw_rescoring": sec}
+                line.setdefault("secondary", {})["sw_rescoring"] = sec
                 sjob.close()
             except Exception as e:  # pragma: no cover
-                line["secondary"] = {"error": repr(e)}
+                line.setdefault("secondary", {})["sw_rescoring"] = {"error": repr(e)}
 
         # ---- secondary: nucleotide gapped aligner (config[4] shape in miniature: 150-bp reads vs genome pieces) ------------
         if not args.no_secondary and world == 1:

@@ -22,7 +22,7 @@ namespace {
 constexpr int KSW_NEG_INF = -0x40000000;
 constexpr int EZ_SCORE_ONLY = 0x01, EZ_EXTZ_ONLY = 0x40;
 constexpr int NUCL_WARPS = 8;
-constexpr int MAX_CHUNKS = 4;  // a rounded band row spans at most 4 x 32 lanes (w <= 64 -> <= 96)
+constexpr int MAX_CHUNKS = 3;  // band 64: at most 65 cells per anti-diagonal, rounded outwards to 16 -> at most 96 lanes
 
 struct NuclTask { uint32_t query; uint32_t target; uint32_t diagonal; uint32_t cigar_off; };
 
