@@ -398,6 +398,13 @@ def main():
         except Exception:
             roof["hbm"]["peak_gbs"] = 6650.0
             roof["hbm"]["peak_source"] = "fallback"
+        try:   # DRAM traffic of the dominant launch, from the committed ncu capture of this same command
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["ungapped_scan_kernel<16,12>"]
+            roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            roof["traffic_note"] = "bytes per launch of ungapped_scan_kernel<16,12> (%d of the 16 queries), ncu capture in profiles/; algorithmic %d" % (
+                tr["queries_in_launch"], tr["algorithmic_bytes"])
+        except Exception:
+            pass
         if dpx:
             peak = dpx * info["sm_count"] * clk_mhz * 1e6 / 1e12
             roof["peak"] = peak
