@@ -580,14 +580,17 @@ __device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t se
 // FIND (end positions for known scores): target = packed scores of the two targets (0xFFFF = half not wanted); every lane
 // records, per half, the first column in which one of its rows equals the score and the smallest such row
 // (key = col << 16 | row); the scan stops 31 steps after every wanted half has been seen somewhere in the warp.
-template <int K, bool FIRST, bool FIND>
+// REV (start positions): the two halves read the REVERSED profile copy at their own, arbitrarily aligned row offsets
+// (pptr / pptr_b: byte loads instead of vector loads) and walk their targets backwards from dbEnd (pa_t/pb_t point at it).
+template <int K, bool FIRST, bool FIND, bool REV = false>
 __device__ __forceinline__ uint32_t sw16_tile(const int8_t *pptr, int Lp, const uint8_t *pa_t, const uint8_t *pb_t, int tla,
                                               int tlb, int ncols, int A, uint32_t neg_ge2, uint32_t neg_go2,
                                               const uint2 *bnd_rd, uint2 *bnd_wr, bool write_bnd, uint32_t best,
                                               uint32_t target = 0, int row_base = 0, uint32_t *key_lo = nullptr,
-                                              uint32_t *key_hi = nullptr) {
+                                              uint32_t *key_hi = nullptr, const int8_t *pptr_b = nullptr) {
     static_assert(K % 4 == 0 && K <= 16, "K in {4,8,12,16}");
     constexpr int W = K / 4;
+    constexpr int TDIR = REV ? -1 : 1;
     const int lane = threadIdx.x & 31;
     const uint32_t padres = (uint32_t) A | ((uint32_t) A << 8);
     // State per row: H (previous column) and Eh = E + go.  F travels down the column as Fh = F + go.
@@ -609,8 +612,8 @@ __device__ __forceinline__ uint32_t sw16_tile(const int8_t *pptr, int Lp, const 
     for (int step = 0; step < nsteps; step++) {
         if ((step & 31) == 0) {
             const int c = step + lane;
-            const uint32_t ra = (c < tla) ? (uint32_t) pa_t[c] : (uint32_t) A;
-            const uint32_t rb = (c < tlb) ? (uint32_t) pb_t[c] : (uint32_t) A;
+            const uint32_t ra = (c < tla) ? (uint32_t) pa_t[c * TDIR] : (uint32_t) A;
+            const uint32_t rb = (c < tlb) ? (uint32_t) pb_t[c * TDIR] : (uint32_t) A;
             tchunk = ra | (rb << 8);
             if (!FIRST) bchunk = (c < ncols) ? bnd_rd[c] : make_uint2(0, 0);
         }
@@ -625,9 +628,12 @@ __device__ __forceinline__ uint32_t sw16_tile(const int8_t *pptr, int Lp, const 
         } else if (lane == 0) { hin = 0; fin = 0; }
         if (lane == 0) res = r0;
         const int8_t *ppa = pptr + (res & 0xffu) * (uint32_t) Lp;
-        const int8_t *ppb = pptr + (res >> 8) * (uint32_t) Lp;
-        uint32_t wa[W], wb[W];
-        if constexpr (K == 16) {
+        const int8_t *ppb = (REV ? pptr_b : pptr) + (res >> 8) * (uint32_t) Lp;
+        uint32_t wa[REV ? K : W], wb[REV ? K : W];
+        if constexpr (REV) {
+#pragma unroll
+            for (int j = 0; j < K; j++) { wa[j] = (uint8_t) ppa[j]; wb[j] = (uint8_t) ppb[j]; }
+        } else if constexpr (K == 16) {
             const uint4 va = *reinterpret_cast<const uint4 *>(ppa), vb = *reinterpret_cast<const uint4 *>(ppb);
             wa[0] = va.x; wa[1] = va.y; wa[2] = va.z; wa[3] = va.w;
             wb[0] = vb.x; wb[1] = vb.y; wb[2] = vb.z; wb[3] = vb.w;
@@ -644,7 +650,7 @@ __device__ __forceinline__ uint32_t sw16_tile(const int8_t *pptr, int Lp, const 
         constexpr uint32_t SEL[4] = {0xC480u, 0xD591u, 0xE6A2u, 0xF7B3u};
 #pragma unroll
         for (int j = K - 1; j >= 0; j--) {
-            const uint32_t sc = prmt_b32(wa[j >> 2], wb[j >> 2], SEL[j & 3]);
+            const uint32_t sc = REV ? prmt_b32(wa[j], wb[j], SEL[0]) : prmt_b32(wa[j >> 2], wb[j >> 2], SEL[j & 3]);
             Eh[j] = __viaddmax_s16x2(Eh[j], neg_ge2, H[j]);
             const uint32_t e = __vadd2(Eh[j], neg_go2);
             H[j] = __viaddmax_s16x2_relu(j > 0 ? H[j - 1] : hdiag_in, sc, e);
@@ -697,30 +703,31 @@ __device__ __forceinline__ uint32_t sw16_tile(const int8_t *pptr, int Lp, const 
     return best;
 }
 
-template <int K, bool FIND>
+template <int K, bool FIND, bool REV>
 __device__ __forceinline__ uint32_t sw16_tile_any(bool first, const int8_t *pptr, int Lp, const uint8_t *pa_t, const uint8_t *pb_t,
                                                   int tla, int tlb, int ncols, int A, uint32_t neg_ge2, uint32_t neg_go2,
                                                   const uint2 *bnd_rd, uint2 *bnd_wr, bool write_bnd, uint32_t best,
                                                   uint32_t target = 0, int row_base = 0, uint32_t *key_lo = nullptr,
-                                                  uint32_t *key_hi = nullptr) {
-    if (first) return sw16_tile<K, true, FIND>(pptr, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, write_bnd, best,
-                                               target, row_base, key_lo, key_hi);
-    return sw16_tile<K, false, FIND>(pptr, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, write_bnd, best, target,
-                                     row_base, key_lo, key_hi);
+                                                  uint32_t *key_hi = nullptr, const int8_t *pptr_b = nullptr) {
+    if (first) return sw16_tile<K, true, FIND, REV>(pptr, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, write_bnd,
+                                                    best, target, row_base, key_lo, key_hi, pptr_b);
+    return sw16_tile<K, false, FIND, REV>(pptr, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, write_bnd, best,
+                                          target, row_base, key_lo, key_hi, pptr_b);
 }
 
 // All pairs of one work item.  The query is cut into full 512-row tiles (16 rows per lane) plus one last tile whose
 // rows-per-lane flavour (4/8/12/16, item.pad_) is the smallest that covers the remainder.
-template <bool SMEM, bool FIND>
+// MODE 0: score.  MODE 1: end positions for known scores (forward).  MODE 2: start positions -- the same search on the
+// reversed prefixes query[qEnd..0] x target[dbEnd..0] (alignStartPosBacktrace, StripedSmithWaterman.cpp:1129-1212).
+template <bool SMEM, int MODE>
 __device__ __forceinline__ void sw16_item(const int8_t *prof_base, const QueryDesc &q, const WorkItem &item,
                                           const PairDesc *__restrict__ pairs, const uint8_t *__restrict__ db,
                                           const uint64_t *__restrict__ off, const int32_t *__restrict__ len, int A, int go,
                                           int ge, uint2 *bnd0, uint2 *bnd1, unsigned *next_pair_ptr, int32_t *__restrict__ out) {
+    constexpr bool FIND = MODE != 0, REV = MODE == 2;
     const int lane = threadIdx.x & 31;
     const int Lp = q.Lp;
     const uint32_t neg_ge2 = pack16(-ge, -ge), neg_go2 = pack16(-go, -go);
-    const int n_full = (q.qlen - 1) / 512;  // tiles of 512 rows before the last tile
-    const int k_last = (int) item.pad_;
     while (true) {
         unsigned p = 0;
         if (lane == 0) p = atomicAdd(next_pair_ptr, 2u);
@@ -729,8 +736,20 @@ __device__ __forceinline__ void sw16_item(const int8_t *prof_base, const QueryDe
         const bool has_b = p + 1 < item.p1;
         const PairDesc pda = pairs[p], pdb = has_b ? pairs[p + 1] : pairs[p];
         const uint32_t ta = pda.target, tb = pdb.target;
-        const int tla = len[ta], tlb = has_b ? len[tb] : 0;
+        int tla, tlb, nrows, offa = 0, offb = 0;
         const uint8_t *pa_t = db + off[ta], *pb_t = db + off[tb];
+        if (REV) {
+            tla = pda.dbend + 1; tlb = has_b ? pdb.dbend + 1 : 0;
+            pa_t += pda.dbend; pb_t += pdb.dbend;
+            offa = q.qlen - 1 - pda.qend; offb = q.qlen - 1 - pdb.qend;
+            nrows = max(pda.qend + 1, has_b ? pdb.qend + 1 : 0);
+        } else {
+            tla = len[ta]; tlb = has_b ? len[tb] : 0;
+            nrows = q.qlen;
+        }
+        const int n_full = (nrows - 1) / 512;                  // tiles of 512 rows before the last tile
+        const int rem = nrows - n_full * 512;                  // 1..512 rows in the last tile
+        const int k_last = REV ? min(16, ((rem + 31) / 32 + 3) / 4 * 4) : (int) item.pad_;
         int ncols = max(tla, tlb);
         uint32_t best = 0;
         uint32_t target = 0, key_lo = 0xffffffffu, key_hi = 0xffffffffu, gkey_lo = 0xffffffffu, gkey_hi = 0xffffffffu;
@@ -740,12 +759,15 @@ __device__ __forceinline__ void sw16_item(const int8_t *prof_base, const QueryDe
             uint2 *bnd_wr = (tile & 1) ? bnd1 : bnd0;
             const bool last = tile == n_full;
             const int kk = last ? k_last : 16;
-            const int8_t *pl = prof_base + tile * 512 + lane * kk;
+            // REV: a half whose rectangle has fewer rows than its partner's keeps reading, so clamp into the pad columns
+            // at the end of the profile row (everything beyond the half's own rows must read as pad anyway)
+            const int8_t *pl = prof_base + min(offa + tile * 512 + lane * kk, Lp - 16);
+            const int8_t *plb = prof_base + min(offb + tile * 512 + lane * kk, Lp - 16);
             switch (kk) {
-                case 4: best = sw16_tile_any<4, FIND>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi); break;
-                case 8: best = sw16_tile_any<8, FIND>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi); break;
-                case 12: best = sw16_tile_any<12, FIND>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi); break;
-                default: best = sw16_tile_any<16, FIND>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi); break;
+                case 4: best = sw16_tile_any<4, FIND, REV>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi, plb); break;
+                case 8: best = sw16_tile_any<8, FIND, REV>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi, plb); break;
+                case 12: best = sw16_tile_any<12, FIND, REV>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi, plb); break;
+                default: best = sw16_tile_any<16, FIND, REV>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi, plb); break;
             }
             if (FIND) {   // earliest (column, row) so far per half; later tiles only need the columns up to it
 #pragma unroll
@@ -775,7 +797,7 @@ __device__ __forceinline__ void sw16_item(const int8_t *prof_base, const QueryDe
 }
 
 // One launch covers every query length: items carry the rows-per-lane flavour (4/8/12/16) chosen for their query.
-template <bool SMEM, int WARPS, bool FIND>
+template <bool SMEM, int WARPS, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS)
 sw16_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd, const WorkItem *__restrict__ items,
             const PairDesc *__restrict__ pairs, const uint8_t *__restrict__ db, const uint64_t *__restrict__ off,
@@ -802,7 +824,7 @@ sw16_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd,
         if (item_idx >= n_items) break;
         const WorkItem item = items[item_idx];
         const QueryDesc q = qd[item.query];
-        const int8_t *gprof = padded + q.pad_off;
+        const int8_t *gprof = padded + (MODE == 2 ? q.rev_off : q.pad_off);
         if (threadIdx.x == 0) next_pair = item.p0;
         if (SMEM) {
             const unsigned bytes = (unsigned) ((A + 1) * q.Lp);
@@ -817,7 +839,7 @@ sw16_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd,
             __syncthreads();
         }
         const int8_t *pb = SMEM ? (const int8_t *) smem_prof : gprof;
-        sw16_item<SMEM, FIND>(pb, q, item, pairs, db, off, len, A, go, ge, bnd0, bnd1, &next_pair, out);
+        sw16_item<SMEM, MODE>(pb, q, item, pairs, db, off, len, A, go, ge, bnd0, bnd1, &next_pair, out);
     }
 }
 
@@ -1434,7 +1456,7 @@ inline void report_end(const int4 &r, int bias, b200_sw_end &o) {
 
 namespace {
 int run_sw16_pass(b200_ctx *ctx, const std::vector<QueryDesc> &h_qd, const b200_query *queries, const b200_pair *pairs, uint64_t n,
-                  const uint8_t *mask, const int32_t *scores, int go, int ge, std::vector<int32_t> &res);
+                  const uint8_t *mask, const int32_t *scores, int go, int ge, std::vector<int32_t> &res, const b200_sw_end *rev_ends = nullptr);
 }
 
 // alignScoreEndPos for a batch: packed score kernel on every pair that is safe in int16, packed FIND pass for the end
@@ -1514,16 +1536,47 @@ static int sw_startpos_locked(b200_ctx *ctx, const b200_query *queries, const st
                 return set_err(ctx, B200_ERR_ARG, "sw_startpos: end positions outside the sequences");
         }
     }
-    SwPlan plan;
-    plan_pairs(ctx, queries, pairs, n, mask.data(), plan);
-    std::vector<int4> res;
-    int rc = run_sw_pass<-1>(ctx, h_qd, pairs, plan, ends, go, ge, res);
-    if (rc != B200_OK) return rc;
-    for (uint32_t s = 0; s < plan.perm.size(); s++) {
-        const uint32_t i = plan.perm[s];
-        if (res[s].x != ends[i].score) return set_err(ctx, B200_ERR_ARG, "sw_startpos: reverse pass did not reproduce the forward score");
-        out[i].dbstart = ends[i].dbend - res[s].y;
-        out[i].qstart = ends[i].qend - res[s].z;
+    // packed reverse pass where the forward pass was packed too (same int16 safety argument), int32 kernel otherwise
+    const int A = ctx->alphabet;
+    std::vector<int> smax(h_qd.size(), 1);
+    for (size_t qi = 0; qi < h_qd.size(); qi++) {
+        int m2 = 1;
+        const int8_t *pr = queries[qi].profile;
+        for (size_t k = 0; k < (size_t) A * queries[qi].qlen; k++) m2 = std::max(m2, (int) pr[k]);
+        smax[qi] = m2;
+    }
+    std::vector<uint8_t> packed(n, 0), rest(n, 0);
+    bool any_packed = false, any_rest = false;
+    for (uint64_t i = 0; i < n; i++) {
+        if (!mask[i]) continue;
+        const int qi = (int) pairs[i].query;
+        const bool ok = go >= ge && (int64_t) std::min(queries[qi].qlen, ctx->h_len[pairs[i].target]) * smax[qi] < 32000;
+        packed[i] = ok; rest[i] = !ok;
+        any_packed |= ok; any_rest |= !ok;
+    }
+    if (any_packed) {
+        std::vector<int32_t> pos(2 * n, -1);
+        int rc = run_sw16_pass(ctx, h_qd, queries, pairs, n, packed.data(), nullptr, go, ge, pos, ends);
+        if (rc != B200_OK) return rc;
+        for (uint64_t i = 0; i < n; i++) {
+            if (!packed[i]) continue;
+            if (pos[2 * i] < 0 || pos[2 * i] > 0xfffe) return set_err(ctx, B200_ERR_ARG, "sw_startpos: reverse pass did not reproduce the forward score");
+            out[i].dbstart = ends[i].dbend - pos[2 * i];
+            out[i].qstart = ends[i].qend - pos[2 * i + 1];
+        }
+    }
+    if (any_rest) {
+        SwPlan plan;
+        plan_pairs(ctx, queries, pairs, n, rest.data(), plan);
+        std::vector<int4> res;
+        int rc = run_sw_pass<-1>(ctx, h_qd, pairs, plan, ends, go, ge, res);
+        if (rc != B200_OK) return rc;
+        for (uint32_t s2 = 0; s2 < plan.perm.size(); s2++) {
+            const uint32_t i = plan.perm[s2];
+            if (res[s2].x != ends[i].score) return set_err(ctx, B200_ERR_ARG, "sw_startpos: reverse pass did not reproduce the forward score");
+            out[i].dbstart = ends[i].dbend - res[s2].y;
+            out[i].qstart = ends[i].qend - res[s2].z;
+        }
     }
     return B200_OK;
 }
@@ -1623,22 +1676,22 @@ int b200_sw_job_create(b200_ctx *ctx, const b200_query *queries, int nq, const b
 // ---- score-only batch (packed int16x2 fast path + int32 fallback) ---------------------------------------------
 namespace {
 
-template <int WARPS, bool FIND>
+template <int WARPS, int MODE>
 int launch_sw16_w(b200_ctx *ctx, const QueryDesc *d_qd, const int8_t *d_pad, size_t smem, int smem_profile, const WorkItem *d_items,
                   uint32_t n_items, const PairDesc *d_pairs, int go, int ge, uint2 *d_bnd, int bnd_stride, int32_t *d_out) {
     int per_sm = 0;
     if (smem_profile) {
-        CU_TRY(ctx, cudaFuncSetAttribute(sw16_kernel<true, WARPS, FIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw16_kernel<true, WARPS, FIND>, WARPS * 32, smem) != cudaSuccess) per_sm = 1;
-    } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw16_kernel<false, WARPS, FIND>, WARPS * 32, 0) != cudaSuccess) per_sm = 1;
+        CU_TRY(ctx, cudaFuncSetAttribute(sw16_kernel<true, WARPS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw16_kernel<true, WARPS, MODE>, WARPS * 32, smem) != cudaSuccess) per_sm = 1;
+    } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sw16_kernel<false, WARPS, MODE>, WARPS * 32, 0) != cudaSuccess) per_sm = 1;
     per_sm = std::max(1, per_sm);
     const unsigned grid = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) ctx->sm_count * per_sm, n_items));
     if (smem_profile)
-        sw16_kernel<true, WARPS, FIND><<<grid, WARPS * 32, smem, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
+        sw16_kernel<true, WARPS, MODE><<<grid, WARPS * 32, smem, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
                                                                          ctx->d_len, ctx->alphabet, go, ge, d_bnd, bnd_stride, n_items,
                                                                          ctx->counter.as<unsigned>(), d_out);
     else
-        sw16_kernel<false, WARPS, FIND><<<grid, WARPS * 32, 0, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
+        sw16_kernel<false, WARPS, MODE><<<grid, WARPS * 32, 0, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
                                                                        ctx->d_len, ctx->alphabet, go, ge, d_bnd, bnd_stride, n_items,
                                                                        ctx->counter.as<unsigned>(), d_out);
     ctx->launches++;
@@ -1656,16 +1709,17 @@ int sw16_warps() {  // CTA width of the packed kernel (pairs per item = 2 x warp
 }
 
 int launch_sw16(b200_ctx *ctx, const QueryDesc *d_qd, const int8_t *d_pad, int max_Lp, const WorkItem *d_items, uint32_t n_items,
-                const PairDesc *d_pairs, int go, int ge, uint2 *d_bnd, int bnd_stride, int32_t *d_out, bool find = false) {
+                const PairDesc *d_pairs, int go, int ge, uint2 *d_bnd, int bnd_stride, int32_t *d_out, int mode = 0) {
     size_t smem = (size_t) (ctx->alphabet + 1) * max_Lp;
     int smem_profile = 1;
     if (smem > (size_t) ctx->max_smem_optin - 1024) { smem = 0; smem_profile = 0; }
     CU_TRY(ctx, ctx->counter.reserve(sizeof(unsigned)));
     CU_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(unsigned), ctx->stream));
-    if (find) return launch_sw16_w<8, true>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out);
+    if (mode == 1) return launch_sw16_w<8, 1>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out);
+    if (mode == 2) return launch_sw16_w<8, 2>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out);
     if (sw16_warps() == 4)
-        return launch_sw16_w<4, false>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out);
-    return launch_sw16_w<8, false>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out);
+        return launch_sw16_w<4, 0>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out);
+    return launch_sw16_w<8, 0>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out);
 }
 
 }  // namespace
@@ -1675,9 +1729,10 @@ namespace {
 
 // packed (int16x2) kernel over the pairs selected by `mask`: score mode (scores == nullptr; res[i] = score) or FIND mode
 // (scores[i] = known score > 0; res[2i], res[2i+1] = end column, end row).  Results land at the caller's pair index.
+// rev_ends != nullptr: reverse (start position) pass from the given end positions; res[2i], res[2i+1] = reverse column, row.
 int run_sw16_pass(b200_ctx *ctx, const std::vector<QueryDesc> &h_qd, const b200_query *queries, const b200_pair *pairs, uint64_t n,
-                  const uint8_t *mask, const int32_t *scores, int go, int ge, std::vector<int32_t> &res) {
-    const bool find = scores != nullptr;
+                  const uint8_t *mask, const int32_t *scores, int go, int ge, std::vector<int32_t> &res, const b200_sw_end *rev_ends) {
+    const bool find = scores != nullptr || rev_ends != nullptr;
     SwPlan plan;
     plan_pairs(ctx, queries, pairs, n, mask, plan, 2u * (uint32_t) (find ? 8 : sw16_warps()));
     const uint32_t m = (uint32_t) plan.perm.size();
@@ -1687,7 +1742,8 @@ int run_sw16_pass(b200_ctx *ctx, const std::vector<QueryDesc> &h_qd, const b200_
     bool multi = false;
     for (uint32_t s = 0; s < m; s++) {
         const uint32_t i = plan.perm[s];
-        h_pd[s].target = pairs[i].target; h_pd[s].qend = 0; h_pd[s].dbend = 0; h_pd[s].score = find ? scores[i] : 0;
+        h_pd[s].target = pairs[i].target; h_pd[s].qend = 0; h_pd[s].dbend = 0; h_pd[s].score = scores ? scores[i] : 0;
+        if (rev_ends) { h_pd[s].qend = rev_ends[i].qend; h_pd[s].dbend = rev_ends[i].dbend; h_pd[s].score = rev_ends[i].score; }
         max_cols = std::max(max_cols, ctx->h_len[pairs[i].target]);
         max_Lp = std::max(max_Lp, h_qd[pairs[i].query].Lp);
         if (h_qd[pairs[i].query].qlen > 512) multi = true;
@@ -1701,7 +1757,7 @@ int run_sw16_pass(b200_ctx *ctx, const std::vector<QueryDesc> &h_qd, const b200_
     CU_TRY(ctx, cudaMemcpyAsync(ctx->pairs.p, h_pd.data(), sizeof(PairDesc) * m, cudaMemcpyHostToDevice, ctx->stream));
     CU_TRY(ctx, cudaMemcpyAsync(ctx->items.p, plan.items.data(), sizeof(WorkItem) * n_items, cudaMemcpyHostToDevice, ctx->stream));
     int rc = launch_sw16(ctx, ctx->qdesc.as<QueryDesc>(), ctx->pad.as<int8_t>(), max_Lp, ctx->items.as<WorkItem>(), n_items,
-                         ctx->pairs.as<PairDesc>(), go, ge, ctx->bnd.as<uint2>(), bnd_stride, ctx->out4.as<int32_t>(), find);
+                         ctx->pairs.as<PairDesc>(), go, ge, ctx->bnd.as<uint2>(), bnd_stride, ctx->out4.as<int32_t>(), rev_ends ? 2 : (scores ? 1 : 0));
     if (rc != B200_OK) return rc;
     std::vector<int32_t> h((size_t) m * (find ? 2 : 1));
     CU_TRY(ctx, cudaMemcpyAsync(h.data(), ctx->out4.p, sizeof(int32_t) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));

@@ -42,6 +42,11 @@ def main():
         ends = ctx.sw_score_endpos(profs, spairs)
         dt = time.perf_counter() - t0
     print("e2e sw_score_endpos (packed score + packed FIND): %.1f ms  %.1f GCUPS" % (dt * 1e3, cells / 1e9 / dt))
+    for rep in range(2):
+        t0 = time.perf_counter()
+        aln = ctx.sw_align(profs, spairs)
+        dt = time.perf_counter() - t0
+    print("e2e sw_align (score + end + start, all pairs): %.1f ms  %.1f GCUPS" % (dt * 1e3, cells / 1e9 / dt))
     sjob = ctx.sw_job(profs, spairs)
     sjob.run(); ctx.sync()
     ctx.event_record(2); sjob.run(); ctx.event_record(3)
