@@ -12,6 +12,7 @@
 #include "b200_internal.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -587,7 +588,7 @@ __device__ __forceinline__ uint32_t sw16_tile(const int8_t *pptr, int Lp, const 
                                               int tlb, int ncols, int A, uint32_t neg_ge2, uint32_t neg_go2,
                                               const uint2 *bnd_rd, uint2 *bnd_wr, bool write_bnd, uint32_t best,
                                               uint32_t target = 0, int row_base = 0, uint32_t *key_lo = nullptr,
-                                              uint32_t *key_hi = nullptr, const int8_t *pptr_b = nullptr) {
+                                              uint32_t *key_hi = nullptr, const int8_t *pptr_b = nullptr, uint32_t rev_shift = 0) {
     static_assert(K % 4 == 0 && K <= 16, "K in {4,8,12,16}");
     constexpr int W = K / 4;
     constexpr int TDIR = REV ? -1 : 1;
@@ -606,9 +607,22 @@ __device__ __forceinline__ uint32_t sw16_tile(const int8_t *pptr, int Lp, const 
     uint32_t hlast = 0, fout = 0, hdiag_in = 0;
     uint32_t res = padres, tchunk = padres;
     uint2 bchunk = make_uint2(0, 0);
-    const int nsteps = ncols + 31;
-    int stop_at = 0x7fffffff;
+    int nsteps = ncols + 31;
+    bool stopping = false;
+    uint32_t tgt = target;
     const bool want_lo = FIND && (target & 0xffffu) != 0xffffu, want_hi = FIND && (target >> 16) != 0xffffu;
+    uint32_t klo = FIND ? *key_lo : 0u, khi = FIND ? *key_hi : 0u;
+    // REV: the rows a half gained by rounding its start down to a word (rev_shift = shift_lo | shift_hi << 8, each 0..3)
+    // sit in lane 0 of the first tile and score as pad there, so they stay 0 like the boundary above row 0
+    uint32_t rv_and[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, rv_or[3] = {0u, 0u, 0u};
+    if (REV && FIRST && lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            if (j < (int) (rev_shift & 0xffu)) { rv_and[j] &= 0xffff0000u; rv_or[j] |= 0x0000ff80u; }
+            if (j < (int) (rev_shift >> 8)) { rv_and[j] &= 0x0000ffffu; rv_or[j] |= 0xff800000u; }
+        }
+    }
+    const int row_lo = row_base + lane * K - (int) (rev_shift & 0xffu), row_hi = row_base + lane * K - (int) (rev_shift >> 8);
     for (int step = 0; step < nsteps; step++) {
         if ((step & 31) == 0) {
             const int c = step + lane;
@@ -629,10 +643,13 @@ __device__ __forceinline__ uint32_t sw16_tile(const int8_t *pptr, int Lp, const 
         if (lane == 0) res = r0;
         const int8_t *ppa = pptr + (res & 0xffu) * (uint32_t) Lp;
         const int8_t *ppb = (REV ? pptr_b : pptr) + (res >> 8) * (uint32_t) Lp;
-        uint32_t wa[REV ? K : W], wb[REV ? K : W];
-        if constexpr (REV) {
+        uint32_t wa[W], wb[W];
+        if constexpr (REV) {   // word aligned only (each half starts at its own row offset rounded down to 4)
 #pragma unroll
-            for (int j = 0; j < K; j++) { wa[j] = (uint8_t) ppa[j]; wb[j] = (uint8_t) ppb[j]; }
+            for (int w = 0; w < W; w++) {
+                wa[w] = reinterpret_cast<const uint32_t *>(ppa)[w];
+                wb[w] = reinterpret_cast<const uint32_t *>(ppb)[w];
+            }
         } else if constexpr (K == 16) {
             const uint4 va = *reinterpret_cast<const uint4 *>(ppa), vb = *reinterpret_cast<const uint4 *>(ppb);
             wa[0] = va.x; wa[1] = va.y; wa[2] = va.z; wa[3] = va.w;
@@ -650,7 +667,8 @@ __device__ __forceinline__ uint32_t sw16_tile(const int8_t *pptr, int Lp, const 
         constexpr uint32_t SEL[4] = {0xC480u, 0xD591u, 0xE6A2u, 0xF7B3u};
 #pragma unroll
         for (int j = K - 1; j >= 0; j--) {
-            const uint32_t sc = REV ? prmt_b32(wa[j], wb[j], SEL[0]) : prmt_b32(wa[j >> 2], wb[j >> 2], SEL[j & 3]);
+            uint32_t sc = prmt_b32(wa[j >> 2], wb[j >> 2], SEL[j & 3]);
+            if (REV && FIRST && j < 3) sc = (sc & rv_and[j]) | rv_or[j];
             Eh[j] = __viaddmax_s16x2(Eh[j], neg_ge2, H[j]);
             const uint32_t e = __vadd2(Eh[j], neg_go2);
             H[j] = __viaddmax_s16x2_relu(j > 0 ? H[j - 1] : hdiag_in, sc, e);
@@ -669,37 +687,38 @@ __device__ __forceinline__ uint32_t sw16_tile(const int8_t *pptr, int Lp, const 
             uint32_t cm = 0;
 #pragma unroll
             for (int j = 0; j < K; j += 2) cm = __vimax3_s16x2(cm, H[j], H[j + 1]);
-            const uint32_t dx = cm ^ target;
-            const bool mlo = (dx & 0xffffu) == 0 && *key_lo == 0xffffffffu;
-            const bool mhi = (dx >> 16) == 0 && *key_hi == 0xffffffffu;
-            if (mlo || mhi) {          // rare: a lane reaches the final score
+            const uint32_t dx = cm ^ tgt;
+            if ((dx & 0xffffu) == 0 || dx < 0x10000u) {          // rare: a lane reaches the final score of a half
                 const int col = step - lane;
-                if (mlo) {
+                if ((dx & 0xffffu) == 0) {
                     int jr = K - 1;
 #pragma unroll
                     for (int j = K - 2; j >= 0; j--) if ((H[j] & 0xffffu) == (target & 0xffffu)) jr = j;
-                    *key_lo = ((uint32_t) col << 16) | (uint32_t) (row_base + lane * K + jr);
+                    klo = ((uint32_t) col << 16) | (uint32_t) (row_lo + jr);
+                    tgt |= 0xffffu;                               // recorded: this half cannot match again
                 }
-                if (mhi) {
+                if (dx < 0x10000u) {
                     int jr = K - 1;
 #pragma unroll
                     for (int j = K - 2; j >= 0; j--) if ((H[j] >> 16) == (target >> 16)) jr = j;
-                    *key_hi = ((uint32_t) col << 16) | (uint32_t) (row_base + lane * K + jr);
+                    khi = ((uint32_t) col << 16) | (uint32_t) (row_hi + jr);
+                    tgt |= 0xffff0000u;
                 }
             }
-            if (stop_at == 0x7fffffff) {
-                const bool seen_lo = !want_lo || __any_sync(0xffffffffu, *key_lo != 0xffffffffu);
-                const bool seen_hi = !want_hi || __any_sync(0xffffffffu, *key_hi != 0xffffffffu);
-                if (seen_lo && seen_hi) stop_at = step + 31;
+            // a late look only delays the stop: by then every lane has passed the recorded column anyway
+            if ((step & 7) == 7 && !stopping) {
+                const bool seen_lo = !want_lo || __any_sync(0xffffffffu, klo != 0xffffffffu);
+                const bool seen_hi = !want_hi || __any_sync(0xffffffffu, khi != 0xffffffffu);
+                if (seen_lo && seen_hi) { stopping = true; nsteps = min(nsteps, step + 32); }
             }
         }
         hlast = H[K - 1];
         fout = f;
         if (write_bnd && lane == 31 && step >= 31) bnd_wr[step - 31] = make_uint2(hlast, f);
         hdiag_in = hin;
-        if (FIND && step >= stop_at) break;
     }
     if (write_bnd) __syncwarp();
+    if (FIND) { *key_lo = klo; *key_hi = khi; }
     return best;
 }
 
@@ -708,11 +727,11 @@ __device__ __forceinline__ uint32_t sw16_tile_any(bool first, const int8_t *pptr
                                                   int tla, int tlb, int ncols, int A, uint32_t neg_ge2, uint32_t neg_go2,
                                                   const uint2 *bnd_rd, uint2 *bnd_wr, bool write_bnd, uint32_t best,
                                                   uint32_t target = 0, int row_base = 0, uint32_t *key_lo = nullptr,
-                                                  uint32_t *key_hi = nullptr, const int8_t *pptr_b = nullptr) {
+                                                  uint32_t *key_hi = nullptr, const int8_t *pptr_b = nullptr, uint32_t rev_shift = 0) {
     if (first) return sw16_tile<K, true, FIND, REV>(pptr, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, write_bnd,
-                                                    best, target, row_base, key_lo, key_hi, pptr_b);
+                                                    best, target, row_base, key_lo, key_hi, pptr_b, rev_shift);
     return sw16_tile<K, false, FIND, REV>(pptr, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, write_bnd, best,
-                                          target, row_base, key_lo, key_hi, pptr_b);
+                                          target, row_base, key_lo, key_hi, pptr_b, rev_shift);
 }
 
 // All pairs of one work item.  The query is cut into full 512-row tiles (16 rows per lane) plus one last tile whose
@@ -723,7 +742,8 @@ template <bool SMEM, int MODE>
 __device__ __forceinline__ void sw16_item(const int8_t *prof_base, const QueryDesc &q, const WorkItem &item,
                                           const PairDesc *__restrict__ pairs, const uint8_t *__restrict__ db,
                                           const uint64_t *__restrict__ off, const int32_t *__restrict__ len, int A, int go,
-                                          int ge, uint2 *bnd0, uint2 *bnd1, unsigned *next_pair_ptr, int32_t *__restrict__ out) {
+                                          int ge, uint2 *bnd0, uint2 *bnd1, unsigned *next_pair_ptr, int32_t *__restrict__ out,
+                                          const int32_t *__restrict__ dv_score, const int32_t *__restrict__ dv_pos) {
     constexpr bool FIND = MODE != 0, REV = MODE == 2;
     const int lane = threadIdx.x & 31;
     const int Lp = q.Lp;
@@ -737,14 +757,37 @@ __device__ __forceinline__ void sw16_item(const int8_t *prof_base, const QueryDe
         const PairDesc pda = pairs[p], pdb = has_b ? pairs[p + 1] : pairs[p];
         const uint32_t ta = pda.target, tb = pdb.target;
         int tla, tlb, nrows, offa = 0, offb = 0;
+        uint32_t rev_shift = 0;
         const uint8_t *pa_t = db + off[ta], *pb_t = db + off[tb];
+        // chained launches (dv_score != nullptr): scores / end positions come from the previous kernel's output in plan
+        // order, PairDesc.qend carries the caller's gate; a half with nothing to find runs with zero columns
+        int sca = pda.score, scb = pdb.score, qea = pda.qend, qeb = pdb.qend, dea = pda.dbend, deb = pdb.dbend;
+        bool wa = true, wb = has_b;
+        if (FIND && dv_score != nullptr) {
+            sca = dv_score[p]; scb = has_b ? dv_score[p + 1] : 0;
+            wa = sca > 0; wb = has_b && scb > 0;
+            if (REV) {
+                wa = wa && pda.qend != 0; wb = wb && pdb.qend != 0;
+                dea = wa ? dv_pos[2 * p] : 0; qea = wa ? dv_pos[2 * p + 1] : 0;
+                deb = wb ? dv_pos[2 * (p + 1)] : 0; qeb = wb ? dv_pos[2 * (p + 1) + 1] : 0;
+            }
+            if (!wa && !wb) {
+                if (lane == 0) {
+                    out[2 * p] = 65535; out[2 * p + 1] = 65535;
+                    if (has_b) { out[2 * (p + 1)] = 65535; out[2 * (p + 1) + 1] = 65535; }
+                }
+                continue;
+            }
+        }
         if (REV) {
-            tla = pda.dbend + 1; tlb = has_b ? pdb.dbend + 1 : 0;
-            pa_t += pda.dbend; pb_t += pdb.dbend;
-            offa = q.qlen - 1 - pda.qend; offb = q.qlen - 1 - pdb.qend;
-            nrows = max(pda.qend + 1, has_b ? pdb.qend + 1 : 0);
+            tla = wa ? dea + 1 : 0; tlb = wb ? deb + 1 : 0;
+            pa_t += dea; pb_t += deb;
+            offa = q.qlen - 1 - qea; offb = q.qlen - 1 - qeb;
+            rev_shift = (uint32_t) (offa & 3) | ((uint32_t) (offb & 3) << 8);   // word-align each half's first profile row
+            offa &= ~3; offb &= ~3;
+            nrows = max(wa ? qea + 1 + (int) (rev_shift & 0xffu) : 0, wb ? qeb + 1 + (int) (rev_shift >> 8) : 0);
         } else {
-            tla = len[ta]; tlb = has_b ? len[tb] : 0;
+            tla = wa ? len[ta] : 0; tlb = wb ? len[tb] : 0;
             nrows = q.qlen;
         }
         const int n_full = (nrows - 1) / 512;                  // tiles of 512 rows before the last tile
@@ -753,7 +796,7 @@ __device__ __forceinline__ void sw16_item(const int8_t *prof_base, const QueryDe
         int ncols = max(tla, tlb);
         uint32_t best = 0;
         uint32_t target = 0, key_lo = 0xffffffffu, key_hi = 0xffffffffu, gkey_lo = 0xffffffffu, gkey_hi = 0xffffffffu;
-        if (FIND) target = ((uint32_t) pda.score & 0xffffu) | ((has_b ? (uint32_t) pdb.score & 0xffffu : 0xffffu) << 16);
+        if (FIND) target = (wa ? (uint32_t) sca & 0xffffu : 0xffffu) | ((wb ? (uint32_t) scb & 0xffffu : 0xffffu) << 16);
         for (int tile = 0; tile <= n_full; tile++) {
             const uint2 *bnd_rd = (tile & 1) ? bnd0 : bnd1;
             uint2 *bnd_wr = (tile & 1) ? bnd1 : bnd0;
@@ -764,10 +807,10 @@ __device__ __forceinline__ void sw16_item(const int8_t *prof_base, const QueryDe
             const int8_t *pl = prof_base + min(offa + tile * 512 + lane * kk, Lp - 16);
             const int8_t *plb = prof_base + min(offb + tile * 512 + lane * kk, Lp - 16);
             switch (kk) {
-                case 4: best = sw16_tile_any<4, FIND, REV>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi, plb); break;
-                case 8: best = sw16_tile_any<8, FIND, REV>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi, plb); break;
-                case 12: best = sw16_tile_any<12, FIND, REV>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi, plb); break;
-                default: best = sw16_tile_any<16, FIND, REV>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi, plb); break;
+                case 4: best = sw16_tile_any<4, FIND, REV>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi, plb, rev_shift); break;
+                case 8: best = sw16_tile_any<8, FIND, REV>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi, plb, rev_shift); break;
+                case 12: best = sw16_tile_any<12, FIND, REV>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi, plb, rev_shift); break;
+                default: best = sw16_tile_any<16, FIND, REV>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi, plb, rev_shift); break;
             }
             if (FIND) {   // earliest (column, row) so far per half; later tiles only need the columns up to it
 #pragma unroll
@@ -802,7 +845,8 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS)
 sw16_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd, const WorkItem *__restrict__ items,
             const PairDesc *__restrict__ pairs, const uint8_t *__restrict__ db, const uint64_t *__restrict__ off,
             const int32_t *__restrict__ len, int A, int go, int ge, uint2 *__restrict__ bnd, int bnd_stride,
-            unsigned n_items, unsigned *__restrict__ item_counter, int32_t *__restrict__ out) {
+            unsigned n_items, unsigned *__restrict__ item_counter, int32_t *__restrict__ out,
+            const int32_t *__restrict__ dv_score, const int32_t *__restrict__ dv_pos) {
     extern __shared__ __align__(16) int8_t smem_prof[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ unsigned next_pair;
@@ -839,7 +883,7 @@ sw16_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd,
             __syncthreads();
         }
         const int8_t *pb = SMEM ? (const int8_t *) smem_prof : gprof;
-        sw16_item<SMEM, MODE>(pb, q, item, pairs, db, off, len, A, go, ge, bnd0, bnd1, &next_pair, out);
+        sw16_item<SMEM, MODE>(pb, q, item, pairs, db, off, len, A, go, ge, bnd0, bnd1, &next_pair, out, dv_score, dv_pos);
     }
 }
 
@@ -1457,12 +1501,16 @@ inline void report_end(const int4 &r, int bias, b200_sw_end &o) {
 namespace {
 int run_sw16_pass(b200_ctx *ctx, const std::vector<QueryDesc> &h_qd, const b200_query *queries, const b200_pair *pairs, uint64_t n,
                   const uint8_t *mask, const int32_t *scores, int go, int ge, std::vector<int32_t> &res, const b200_sw_end *rev_ends = nullptr);
+int run_sw16_chain(b200_ctx *ctx, const std::vector<QueryDesc> &h_qd, const b200_query *queries, const b200_pair *pairs, uint64_t n,
+                   const uint8_t *mask, const uint8_t *gate, bool want_start, int go, int ge, std::vector<int32_t> &score,
+                   std::vector<int32_t> &endpos, std::vector<int32_t> *startpos);
 }
 
 // alignScoreEndPos for a batch: packed score kernel on every pair that is safe in int16, packed FIND pass for the end
 // positions of those with a positive score, int32 kernel (score + end in one pass) for the rest.
 static int sw_score_endpos_locked(b200_ctx *ctx, const std::vector<QueryDesc> &h_qd, const b200_query *queries, const b200_pair *pairs,
-                                  uint64_t n, int go, int ge, b200_sw_end *out) {
+                                  uint64_t n, int go, int ge, b200_sw_end *out, const uint8_t *gate = nullptr,
+                                  std::vector<int32_t> *startpos = nullptr, std::vector<uint8_t> *packed_out = nullptr) {
     const int A = ctx->alphabet;
     const int nq = (int) h_qd.size();
     std::vector<int> smax(nq, 1);
@@ -1483,16 +1531,12 @@ static int sw_score_endpos_locked(b200_ctx *ctx, const std::vector<QueryDesc> &h
     }
     std::vector<int4> res4(n, make_int4(0, -1, -1, 0));
     if (any_packed) {
+        // score -> end positions (-> start positions) as chained launches over one plan: nothing returns to the host in between
         std::vector<int32_t> score(n, 0), pos(2 * n, -1);
-        int rc = run_sw16_pass(ctx, h_qd, queries, pairs, n, packed.data(), nullptr, go, ge, score);
+        if (startpos != nullptr) startpos->assign(2 * n, -1);
+        int rc = run_sw16_chain(ctx, h_qd, queries, pairs, n, any_rest ? packed.data() : nullptr, gate, startpos != nullptr, go, ge,
+                                score, pos, startpos);
         if (rc != B200_OK) return rc;
-        std::vector<uint8_t> need(n);
-        bool any_need = false;
-        for (uint64_t i = 0; i < n; i++) { need[i] = (packed[i] && score[i] > 0) ? 1 : 0; any_need |= need[i] != 0; }
-        if (any_need) {
-            rc = run_sw16_pass(ctx, h_qd, queries, pairs, n, need.data(), score.data(), go, ge, pos);
-            if (rc != B200_OK) return rc;
-        }
         for (uint64_t i = 0; i < n; i++)
             if (packed[i] && score[i] > 0) res4[i] = make_int4(score[i], pos[2 * i], pos[2 * i + 1], 0);
     }
@@ -1505,6 +1549,7 @@ static int sw_score_endpos_locked(b200_ctx *ctx, const std::vector<QueryDesc> &h
         for (uint32_t s = 0; s < plan.perm.size(); s++) res4[plan.perm[s]] = res[s];
     }
     for (uint64_t i = 0; i < n; i++) report_end(res4[i], queries[pairs[i].query].bias, out[i]);
+    if (packed_out != nullptr) packed_out->swap(packed);
     return B200_OK;
 }
 
@@ -1524,12 +1569,12 @@ int b200_sw_score_endpos(b200_ctx *ctx, const b200_query *queries, int nq, const
 }
 
 static int sw_startpos_locked(b200_ctx *ctx, const b200_query *queries, const std::vector<QueryDesc> &h_qd, const b200_pair *pairs, uint64_t n, int go,
-                              int ge, const b200_sw_end *ends, const uint8_t *gate, b200_sw_aln *out) {
+                              int ge, const b200_sw_end *ends, const uint8_t *gate, b200_sw_aln *out, const uint8_t *skip = nullptr) {
     std::vector<uint8_t> mask(n);
     for (uint64_t i = 0; i < n; i++) {
         out[i].score = ends[i].score; out[i].qend = ends[i].qend; out[i].dbend = ends[i].dbend; out[i].word = ends[i].word;
         out[i].qstart = -1; out[i].dbstart = -1;
-        mask[i] = (ends[i].dbend != -1 && (gate == nullptr || gate[i])) ? 1 : 0;
+        mask[i] = (ends[i].dbend != -1 && (gate == nullptr || gate[i]) && (skip == nullptr || !skip[i])) ? 1 : 0;
         if (mask[i]) {
             const int ql = h_qd[pairs[i].query].qlen, tl = ctx->h_len[pairs[i].target];
             if (ends[i].qend < 0 || ends[i].qend >= ql || ends[i].dbend < 0 || ends[i].dbend >= tl || ends[i].score <= 0)
@@ -1609,9 +1654,22 @@ int b200_sw_align(b200_ctx *ctx, const b200_query *queries, int nq, const b200_p
     rc = stage_queries(ctx, queries, nq, true, h_qd);
     if (rc != B200_OK) return rc;
     std::vector<b200_sw_end> ends(n);
-    rc = sw_score_endpos_locked(ctx, h_qd, queries, pairs, n, go, ge, ends.data());
+    std::vector<int32_t> startpos;
+    std::vector<uint8_t> packed;
+    rc = sw_score_endpos_locked(ctx, h_qd, queries, pairs, n, go, ge, ends.data(), gate, &startpos, &packed);
     if (rc != B200_OK) return rc;
-    return sw_startpos_locked(ctx, queries, h_qd, pairs, n, go, ge, ends.data(), gate, out);
+    // the packed pairs already carry their start positions; the int32 reverse kernel covers the rest
+    rc = sw_startpos_locked(ctx, queries, h_qd, pairs, n, go, ge, ends.data(), gate, out, packed.data());
+    if (rc != B200_OK) return rc;
+    if (!startpos.empty())
+        for (uint64_t i = 0; i < n; i++) {
+            if (!packed[i] || ends[i].dbend == -1 || (gate != nullptr && !gate[i])) continue;
+            if (startpos[2 * i] < 0 || startpos[2 * i] > 0xfffe)
+                return set_err(ctx, B200_ERR_CUDA, "sw_align: reverse pass did not reproduce the forward score");
+            out[i].dbstart = ends[i].dbend - startpos[2 * i];
+            out[i].qstart = ends[i].qend - startpos[2 * i + 1];
+        }
+    return B200_OK;
 }
 
 // ---- resident SW job (forward score + end positions) -----------------------------------------------------
@@ -1678,7 +1736,8 @@ namespace {
 
 template <int WARPS, int MODE>
 int launch_sw16_w(b200_ctx *ctx, const QueryDesc *d_qd, const int8_t *d_pad, size_t smem, int smem_profile, const WorkItem *d_items,
-                  uint32_t n_items, const PairDesc *d_pairs, int go, int ge, uint2 *d_bnd, int bnd_stride, int32_t *d_out) {
+                  uint32_t n_items, const PairDesc *d_pairs, int go, int ge, uint2 *d_bnd, int bnd_stride, int32_t *d_out,
+                  const int32_t *dv_score = nullptr, const int32_t *dv_pos = nullptr) {
     int per_sm = 0;
     if (smem_profile) {
         CU_TRY(ctx, cudaFuncSetAttribute(sw16_kernel<true, WARPS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -1689,11 +1748,11 @@ int launch_sw16_w(b200_ctx *ctx, const QueryDesc *d_qd, const int8_t *d_pad, siz
     if (smem_profile)
         sw16_kernel<true, WARPS, MODE><<<grid, WARPS * 32, smem, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
                                                                          ctx->d_len, ctx->alphabet, go, ge, d_bnd, bnd_stride, n_items,
-                                                                         ctx->counter.as<unsigned>(), d_out);
+                                                                         ctx->counter.as<unsigned>(), d_out, dv_score, dv_pos);
     else
         sw16_kernel<false, WARPS, MODE><<<grid, WARPS * 32, 0, ctx->stream>>>(d_pad, d_qd, d_items, d_pairs, ctx->d_res, ctx->d_off,
                                                                        ctx->d_len, ctx->alphabet, go, ge, d_bnd, bnd_stride, n_items,
-                                                                       ctx->counter.as<unsigned>(), d_out);
+                                                                       ctx->counter.as<unsigned>(), d_out, dv_score, dv_pos);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
     return B200_OK;
@@ -1709,14 +1768,15 @@ int sw16_warps() {  // CTA width of the packed kernel (pairs per item = 2 x warp
 }
 
 int launch_sw16(b200_ctx *ctx, const QueryDesc *d_qd, const int8_t *d_pad, int max_Lp, const WorkItem *d_items, uint32_t n_items,
-                const PairDesc *d_pairs, int go, int ge, uint2 *d_bnd, int bnd_stride, int32_t *d_out, int mode = 0) {
+                const PairDesc *d_pairs, int go, int ge, uint2 *d_bnd, int bnd_stride, int32_t *d_out, int mode = 0,
+                const int32_t *dv_score = nullptr, const int32_t *dv_pos = nullptr) {
     size_t smem = (size_t) (ctx->alphabet + 1) * max_Lp;
     int smem_profile = 1;
     if (smem > (size_t) ctx->max_smem_optin - 1024) { smem = 0; smem_profile = 0; }
     CU_TRY(ctx, ctx->counter.reserve(sizeof(unsigned)));
     CU_TRY(ctx, cudaMemsetAsync(ctx->counter.p, 0, sizeof(unsigned), ctx->stream));
-    if (mode == 1) return launch_sw16_w<8, 1>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out);
-    if (mode == 2) return launch_sw16_w<8, 2>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out);
+    if (mode == 1) return launch_sw16_w<8, 1>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out, dv_score, dv_pos);
+    if (mode == 2) return launch_sw16_w<8, 2>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out, dv_score, dv_pos);
     if (sw16_warps() == 4)
         return launch_sw16_w<4, 0>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out);
     return launch_sw16_w<8, 0>(ctx, d_qd, d_pad, smem, smem_profile, d_items, n_items, d_pairs, go, ge, d_bnd, bnd_stride, d_out);
@@ -1766,6 +1826,73 @@ int run_sw16_pass(b200_ctx *ctx, const std::vector<QueryDesc> &h_qd, const b200_
         const uint32_t i = plan.perm[s];
         if (find) { res[2 * (size_t) i] = h[2 * (size_t) s]; res[2 * (size_t) i + 1] = h[2 * (size_t) s + 1]; }
         else res[i] = h[s];
+    }
+    return B200_OK;
+}
+
+// score -> FIND -> (reverse) over ONE plan and ONE upload: each launch reads the previous one's output on the device in plan
+// order (dv_score / dv_pos), so the host only sees the final scores and positions.  PairDesc.qend carries the gate of the
+// reverse pass.  score[i], endpos[2i..], startpos[2i..] land at the caller's pair index for the pairs selected by mask.
+int run_sw16_chain(b200_ctx *ctx, const std::vector<QueryDesc> &h_qd, const b200_query *queries, const b200_pair *pairs, uint64_t n,
+                   const uint8_t *mask, const uint8_t *gate, bool want_start, int go, int ge, std::vector<int32_t> &score,
+                   std::vector<int32_t> &endpos, std::vector<int32_t> *startpos) {
+    static const bool trace = getenv("B200_TRACE") != nullptr;   // stderr timing of the phases (development aid)
+    const auto t_begin = std::chrono::steady_clock::now();
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    SwPlan plan;
+    plan_pairs(ctx, queries, pairs, n, mask, plan, 2u * (uint32_t) sw16_warps());
+    const auto t_plan = std::chrono::steady_clock::now();
+    const uint32_t m = (uint32_t) plan.perm.size();
+    if (m == 0) return B200_OK;
+    std::vector<PairDesc> h_pd(m);
+    int max_cols = 1, max_Lp = 0;
+    bool multi = false;
+    for (uint32_t s = 0; s < m; s++) {
+        const uint32_t i = plan.perm[s];
+        h_pd[s].target = pairs[i].target; h_pd[s].qend = (gate == nullptr || gate[i]) ? 1 : 0; h_pd[s].dbend = 0; h_pd[s].score = 0;
+        max_cols = std::max(max_cols, ctx->h_len[pairs[i].target]);
+        max_Lp = std::max(max_Lp, h_qd[pairs[i].query].Lp);
+        if (h_qd[pairs[i].query].qlen > 512) multi = true;
+    }
+    const uint32_t n_items = (uint32_t) plan.items.size();
+    const int bnd_stride = multi ? (int) round_up((uint64_t) max_cols, 32) + 32 : 32;
+    const size_t words = (size_t) m * (want_start ? 5 : 3);   // [score | end (col,row) | start (col,row)]
+    CU_TRY(ctx, ctx->pairs.reserve(sizeof(PairDesc) * m));
+    CU_TRY(ctx, ctx->items.reserve(sizeof(WorkItem) * n_items));
+    CU_TRY(ctx, ctx->out4.reserve(sizeof(int32_t) * words));
+    CU_TRY(ctx, ctx->bnd.reserve(sizeof(int2) * 2 * (size_t) bnd_stride * std::min<uint64_t>(n_items, sw_max_grid(ctx)) * 8));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->pairs.p, h_pd.data(), sizeof(PairDesc) * m, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->items.p, plan.items.data(), sizeof(WorkItem) * n_items, cudaMemcpyHostToDevice, ctx->stream));
+    int32_t *d_score = ctx->out4.as<int32_t>(), *d_end = d_score + m, *d_start = d_score + 3 * (size_t) m;
+    if (trace) { for (auto &e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], ctx->stream); }
+    for (int mode = 0; mode <= (want_start ? 2 : 1); mode++) {
+        int rc = launch_sw16(ctx, ctx->qdesc.as<QueryDesc>(), ctx->pad.as<int8_t>(), max_Lp, ctx->items.as<WorkItem>(), n_items,
+                             ctx->pairs.as<PairDesc>(), go, ge, ctx->bnd.as<uint2>(), bnd_stride,
+                             mode == 0 ? d_score : (mode == 1 ? d_end : d_start), mode, mode ? d_score : nullptr, mode == 2 ? d_end : nullptr);
+        if (rc != B200_OK) return rc;
+        if (trace) cudaEventRecord(ev[mode + 1], ctx->stream);
+    }
+    const auto t_launch = std::chrono::steady_clock::now();
+    std::vector<int32_t> h(words);
+    CU_TRY(ctx, cudaMemcpyAsync(h.data(), ctx->out4.p, sizeof(int32_t) * words, cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const int32_t *he = h.data() + m, *hs = h.data() + 3 * (size_t) m;
+    for (uint32_t s = 0; s < m; s++) {
+        const size_t i = plan.perm[s];
+        score[i] = h[s];
+        endpos[2 * i] = he[2 * (size_t) s]; endpos[2 * i + 1] = he[2 * (size_t) s + 1];
+        if (want_start) { (*startpos)[2 * i] = hs[2 * (size_t) s]; (*startpos)[2 * i + 1] = hs[2 * (size_t) s + 1]; }
+    }
+    if (trace) {
+        const auto t_end = std::chrono::steady_clock::now();
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count(); };
+        float k[3] = {0, 0, 0};
+        for (int mode = 0; mode <= (want_start ? 2 : 1); mode++) cudaEventElapsedTime(&k[mode], ev[mode], ev[mode + 1]);
+        fprintf(stderr, "[b200 trace] sw16 chain: %u pairs, plan %.2f ms, stage+launch %.2f ms, kernels score %.2f / find %.2f / reverse %.2f ms, "
+                        "wait+d2h+scatter %.2f ms, total %.2f ms\n", m, ms(t_begin, t_plan), ms(t_plan, t_launch), k[0], k[1], k[2],
+                ms(t_launch, t_end), ms(t_begin, t_end));
+        for (auto &e : ev) cudaEventDestroy(e);
     }
     return B200_OK;
 }
