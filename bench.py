@@ -470,6 +470,11 @@ def main():
                 ends_host = ctx.sw_score_endpos(sprofs, spairs)   # packed score pass + packed FIND pass, host buffers
                 se_e2e = time.perf_counter() - t0
                 assert np.array_equal(ends_host, ends)
+                ctx.sw_align(sprofs, spairs[:1024])
+                t0 = time.perf_counter()
+                aln_host = ctx.sw_align(sprofs, spairs)   # score -> end -> start positions, three chained packed launches
+                al_e2e = time.perf_counter() - t0
+                assert np.array_equal(aln_host["score"], ends["score"]) and np.array_equal(aln_host["dbend"], ends["dbend"])
                 sclk = clk.stop()
                 assert np.array_equal(sc_job, ends["score"]) and np.array_equal(sc_host, sc_job)
                 sclk_mhz = sclk.get("sm_mhz") or clk_mhz
@@ -482,6 +487,9 @@ def main():
                        "score_endpos": {"value": sw_cells / 1e9 / (sw_ms / 1e3), "unit": METRIC, "kernel": "sw32_kernel<1>", "ms": sw_ms,
                                         "e2e": {"value": sw_cells / 1e9 / se_e2e, "unit": METRIC,
                                                 "path": "b200_sw_score_endpos: sw16 score pass + sw16 FIND pass (end positions), host buffers"}},
+                       "align": {"e2e": {"value": sw_cells / 1e9 / al_e2e, "unit": METRIC, "ms": al_e2e * 1e3,
+                                         "path": "b200_sw_align on every pair: sw16 score -> FIND -> reverse pass chained on the device "
+                                                 "(score, qEnd, dbEnd, qStart, dbStart), host buffers"}},
                        "word_mode_pairs": int(ends["word"].sum()), "clocks": sclk}
                 dpx16 = rates.get("viaddmax_s16x2")
                 if dpx16:

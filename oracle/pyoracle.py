@@ -180,6 +180,44 @@ class Ref:
     def evalue(self, go, ge, db_residues, score, qlen):
         return float(self.lib.ref_evalue(go, ge, ctypes.c_int64(db_residues), ctypes.c_double(score), ctypes.c_double(qlen), None))
 
+    # ---- `align` module at record level (ref_glue.cpp: ref_align_query) ----
+    def align_query(self, q, qkey, tdata, toff, hit_idx, hit_keys, db_residues, comp_bias=True, comp_bias_scale=1.0, go=11, ge=1,
+                    sw_mode=2, eval_thr=1e-3, cov_thr=0.0, cov_mode=0, seq_id_thr=0.0, aln_len_thr=0, seq_id_mode=0,
+                    max_accept=0x7fffffff, max_reject=0x7fffffff, include_identity=False, add_backtrace=True, compress=True):
+        """-> (records text, n getSWResult calls, n accepted)"""
+        q = np.ascontiguousarray(q, np.uint8)
+        hi = np.ascontiguousarray(hit_idx, np.uint32)
+        hk = np.ascontiguousarray(hit_keys, np.uint32)
+        to = np.ascontiguousarray(toff, np.int64)
+        cap = 4096 + len(hi) * 4096
+        out = ctypes.create_string_buffer(cap)
+        na = ctypes.c_int64(0); nacc = ctypes.c_int64(0)
+        self.lib.ref_align_query.restype = ctypes.c_int64
+        n = self.lib.ref_align_query(_p(q), len(q), ctypes.c_uint32(qkey), 1 if comp_bias else 0, ctypes.c_float(comp_bias_scale),
+                                     _p(tdata), _p(to), _p(hi), _p(hk), ctypes.c_int64(len(hi)), ctypes.c_int64(db_residues), go, ge,
+                                     sw_mode, ctypes.c_double(eval_thr), ctypes.c_float(cov_thr), cov_mode, ctypes.c_float(seq_id_thr),
+                                     aln_len_thr, seq_id_mode, ctypes.c_uint32(max_accept), ctypes.c_uint32(max_reject),
+                                     1 if include_identity else 0, 1 if add_backtrace else 0, 1 if compress else 0, out,
+                                     ctypes.c_int64(cap), ctypes.byref(na), ctypes.byref(nacc))
+        if n < 0:
+            raise RuntimeError("ref_align_query: buffer too small")
+        return out.raw[:n], int(na.value), int(nacc.value)
+
+    def result_to_buffer(self, db_key, score, seq_id, evalue, qs, qe, ql, ds, de, dl, backtrace=b"", add_backtrace=False, compress=True):
+        out = ctypes.create_string_buffer(1024 + 2 * len(backtrace))
+        self.lib.ref_result_to_buffer.restype = ctypes.c_int64
+        n = self.lib.ref_result_to_buffer(ctypes.c_uint32(db_key), score, ctypes.c_float(seq_id), ctypes.c_double(evalue), qs, qe, ql, ds, de,
+                                          dl, backtrace, 1 if add_backtrace else 0, 1 if compress else 0, out)
+        return out.raw[:n]
+
+    def prefilter_roundtrip(self, entry):
+        cap = entry.count(b"\n") + 4
+        ids = np.zeros(cap, np.uint32); sc = np.zeros(cap, np.int32); dg = np.zeros(cap, np.uint16)
+        out = ctypes.create_string_buffer(64 * cap)
+        self.lib.ref_prefilter_roundtrip.restype = ctypes.c_int64
+        n = self.lib.ref_prefilter_roundtrip(entry + b"\0", _p(ids), _p(sc), _p(dg), ctypes.c_int64(cap), out)
+        return ids[:n], sc[:n], dg[:n], out.value
+
     def aa2num(self, nucl=False):
         t = np.zeros(256, np.uint8)
         self.lib.ref_aa2num(1 if nucl else 0, _p(t))

@@ -16,6 +16,8 @@
 //   SubstitutionMatrix::calcLocalAaBiasCorrection src/commons/SubstitutionMatrix.cpp:79
 //   BandedNucleotideAligner::align         src/alignment/BandedNucleotideAligner.cpp:73
 //   ksw_extz2_sse                          lib/ksw2/ksw2_extz2_sse.cpp:44
+//   Matcher::getSWResult / resultToBuffer / compareHits  src/alignment/Matcher.cpp:62,282  Matcher.h:161
+//   QueryMatcher::parsePrefilterHit / prefilterHitToBuffer  src/prefiltering/QueryMatcher.h:87,120
 //
 // Link-time stand-ins (the reference needs them only for code we never reach):
 //   block_aligner C API (Rust crate, no cargo in this image)  -> "failed" results, so
@@ -38,6 +40,8 @@
 #include "SequenceLookup.h"
 #include "EvalueComputation.h"
 #include "BandedNucleotideAligner.h"
+#include "Matcher.h"
+#include "QueryMatcher.h"
 #include "ProfileStates.h"
 #include "Util.h"
 #include "Debug.h"
@@ -394,6 +398,99 @@ void ref_banded_nucl_align_batch(const unsigned char *qdata, const int64_t *qoff
 void ref_aa2num(int nucl, unsigned char *table256) {
     BaseMatrix *m = nucl ? (BaseMatrix *) g_nt : (BaseMatrix *) g_aa;
     for (int c = 0; c < 256; c++) table256[c] = m->aa2num[c];
+}
+
+// ---- the `align` module at record level -------------------------------------------------------
+// One query against its prefilter list, as the body of Alignment::run's per-query loop does it (Alignment.cpp:346-403):
+// canBeCovered -> Matcher::getSWResult -> identity override -> checkCriteria -> compareHits -> resultToBuffer.
+// Alignment.cpp itself needs the DB readers, so the ~15 lines of loop control are repeated here around the reference's
+// own Matcher / Util functions; checkCriteria is Alignment.cpp:548-567 verbatim in meaning.
+// hitKeys[i] = database key written into the record, hitIdx[i] = index into tdata/toff.  Returns bytes written to out
+// (records, NUL-terminated) or -1 if cap is too small; *nAligned = getSWResult calls, *nAccepted = records.
+int64_t ref_align_query(const unsigned char *q, int qL, uint32_t qKey, int compBias, float compBiasScale,
+                        const unsigned char *tdata, const int64_t *toff, const uint32_t *hitIdx, const uint32_t *hitKeys,
+                        int64_t nHits, int64_t dbResidues, int gapOpen, int gapExtend, int swMode, double evalThr,
+                        float covThr, int covMode, float seqIdThr, int alnLenThr, int seqIdMode, uint32_t maxAccept,
+                        uint32_t maxReject, int includeIdentity, int addBacktrace, int compress, char *out, int64_t cap,
+                        int64_t *nAligned, int64_t *nAccepted) {
+    size_t maxLen = qL;
+    for (int64_t i = 0; i < nHits; i++) maxLen = std::max(maxLen, (size_t) (toff[hitIdx[i] + 1] - toff[hitIdx[i]]));
+    maxLen += 64;
+    EvalueComputation evaluer((size_t) dbResidues, g_aa, gapOpen, gapExtend);
+    Matcher matcher(Parameters::DBTYPE_AMINO_ACIDS, (int) maxLen, g_aa, &evaluer, compBias != 0, compBiasScale, gapOpen, gapExtend, 0.0f, 40);
+    Sequence qSeq(maxLen, Parameters::DBTYPE_AMINO_ACIDS, g_aa, 0, false, compBias != 0);
+    Sequence dbSeq(maxLen, Parameters::DBTYPE_AMINO_ACIDS, g_aa, 0, false, false);
+    std::string qAscii(qL, 'X');
+    for (int i = 0; i < qL; i++) qAscii[i] = g_aa->num2aa[q[i]];
+    qSeq.mapSequence(0, qKey, qAscii.c_str(), qL);
+    matcher.initQuery(&qSeq);
+    std::vector<Matcher::result_t> swResults;
+    size_t passedNum = 0;
+    unsigned int rejected = 0;
+    int64_t aligned = 0;
+    std::string tAscii;
+    for (int64_t i = 0; i < nHits && passedNum < maxAccept && rejected < maxReject; i++) {
+        const unsigned char *t = tdata + toff[hitIdx[i]];
+        const int tL = (int) (toff[hitIdx[i] + 1] - toff[hitIdx[i]]);
+        tAscii.assign(tL, 'X');
+        for (int k = 0; k < tL; k++) tAscii[k] = g_aa->num2aa[t[k]];
+        dbSeq.mapSequence(hitIdx[i], hitKeys[i], tAscii.c_str(), tL);
+        if (Util::canBeCovered(covThr, covMode, static_cast<float>(qL), static_cast<float>(dbSeq.L)) == false) {
+            rejected++;
+            continue;
+        }
+        const bool isIdentity = (qKey == hitKeys[i] && includeIdentity) ? true : false;
+        Matcher::result_t res = matcher.getSWResult(&dbSeq, 0, false, covMode, covThr, evalThr, swMode, seqIdMode, isIdentity, false);
+        aligned++;
+        if (isIdentity) { res.qcov = 1.0f; res.dbcov = 1.0f; res.seqId = 1.0f; }
+        const bool evalOk = (res.eval <= evalThr);
+        const bool seqIdOK = (res.seqId >= (double) seqIdThr);
+        const bool covOK = Util::hasCoverage(covThr, covMode, res.qcov, res.dbcov);
+        const bool alnLenOK = Util::hasAlignmentLength(alnLenThr, res.alnLength);
+        if (isIdentity || (evalOk && seqIdOK && covOK && alnLenOK)) {
+            swResults.emplace_back(res);
+            passedNum++;
+            rejected = 0;
+        } else {
+            rejected++;
+        }
+    }
+    if (swResults.size() > 1) std::sort(swResults.begin(), swResults.end(), Matcher::compareHits);
+    int64_t used = 0;
+    std::vector<char> buf;
+    for (size_t i = 0; i < swResults.size(); i++) {
+        buf.resize(1024 + 2 * swResults[i].backtrace.size());
+        const size_t len = Matcher::resultToBuffer(buf.data(), swResults[i], addBacktrace != 0, compress != 0, false);
+        if (used + (int64_t) len + 1 > cap) return -1;
+        memcpy(out + used, buf.data(), len);
+        used += (int64_t) len;
+    }
+    out[used] = '\0';
+    if (nAligned) *nAligned = aligned;
+    if (nAccepted) *nAccepted = (int64_t) swResults.size();
+    return used;
+}
+
+// Matcher::resultToBuffer on explicit field values (format quirks such as the seqId == 1.0 case)
+int64_t ref_result_to_buffer(uint32_t dbKey, int score, float seqId, double eval, int qStart, int qEnd, int qLen, int dbStart,
+                             int dbEnd, int dbLen, const char *backtrace, int addBacktrace, int compress, char *out) {
+    Matcher::result_t r(dbKey, score, 0.0f, 0.0f, seqId, eval, 0, qStart, qEnd, qLen, dbStart, dbEnd, dbLen,
+                        std::string(backtrace ? backtrace : ""));
+    return (int64_t) Matcher::resultToBuffer(out, r, addBacktrace != 0, compress != 0, false);
+}
+
+// QueryMatcher::parsePrefilterHits on a NUL-terminated entry -> (seqId, prefScore, diagonal) triples, then
+// prefilterHitToBuffer of each back into out (NUL-terminated).  Returns the number of hits.
+int64_t ref_prefilter_roundtrip(const char *entry, uint32_t *ids, int32_t *scores, uint16_t *diags, int64_t cap, char *out) {
+    std::string copy(entry);
+    std::vector<hit_t> hits = QueryMatcher::parsePrefilterHits(&copy[0]);
+    char *p = out;
+    for (size_t i = 0; i < hits.size() && (int64_t) i < cap; i++) {
+        ids[i] = hits[i].seqId; scores[i] = hits[i].prefScore; diags[i] = hits[i].diagonal;
+        p += QueryMatcher::prefilterHitToBuffer(p, hits[i]);
+    }
+    *p = '\0';
+    return (int64_t) hits.size();
 }
 
 }  // extern "C"
