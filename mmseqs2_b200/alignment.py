@@ -116,11 +116,12 @@ def align_batch(ctx, submat, queries, hit_lists, params, evalue, query_keys=None
     n_aln = ctypes.c_uint64(0)
     # worst case of the backtrace pool: qlen + tlen per accepted hit
     bt_cap = 16
-    if params.sw_mode == SCORE_COV_SEQID:
+    if params.sw_mode == SCORE_COV_SEQID or params.include_identity:   # scoreIdentical leaves an all-M backtrace in every mode
         lens = ctx.db_lengths()
         for qi in range(nq):
             if len(hit_lists[qi]):
-                bt_cap += int(len(queries[qi]) * len(hit_lists[qi]) + lens[np.asarray(hit_lists[qi], np.int64)].sum())
+                ids = np.minimum(np.asarray(hit_lists[qi], np.int64), len(lens) - 1)   # range errors are the library's to report
+                bt_cap += int(len(queries[qi]) * len(hit_lists[qi]) + lens[ids].sum())
     pool = ctypes.create_string_buffer(bt_cap)
     rc = lib.b200_align_batch(ctx.h, _p(mat), _p(pb), int(submat.A), _p(qres), _p(qoff), _p(qk), ctypes.c_uint32(nq), _p(hoff), _p(htg),
                               _p(tk), ctypes.byref(params), ctypes.byref(evalue), _p(res), _p(nres), pool, _u64(bt_cap),

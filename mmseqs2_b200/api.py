@@ -231,6 +231,11 @@ class Context:
         offsets = np.ascontiguousarray(offsets, np.uint64)
         self._check(self.lib.b200_db_load(self.h, _p(residues), _p(offsets), _u64(len(offsets) - 1), int(alphabet)))
         self.n_seq = len(offsets) - 1
+        self._db_len = np.diff(offsets.astype(np.int64))
+
+    def db_lengths(self):
+        """lengths of the loaded target sequences (host copy kept at load time)"""
+        return self._db_len
 
     # ---- A2
     def ungapped_scan(self, queries, min_score_excl=15, max_hits=300, want_dense=False):

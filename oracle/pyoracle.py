@@ -218,6 +218,11 @@ class Ref:
         n = self.lib.ref_prefilter_roundtrip(entry + b"\0", _p(ids), _p(sc), _p(dg), ctypes.c_int64(cap), out)
         return ids[:n], sc[:n], dg[:n], out.value
 
+    def bit_score(self, go, ge, db_residues, score):
+        b = ctypes.c_double(0)
+        self.lib.ref_evalue(go, ge, ctypes.c_int64(db_residues), ctypes.c_double(score), ctypes.c_double(100.0), ctypes.byref(b))
+        return float(b.value)
+
     def aa2num(self, nucl=False):
         t = np.zeros(256, np.uint8)
         self.lib.ref_aa2num(1 if nucl else 0, _p(t))
