@@ -168,6 +168,35 @@ def cpu_reference_gcups(queries, res, off, budget_s, threads):
             "sample": "%d queries x whole %d-sequence DB = %.3g cells in %.1f s" % (nq, len(off64) - 1, cells, dt)}
 
 
+def cpu_reference_align_step(queries, tdata, toff, lists, gpu_results, gpu_pool, budget_s, threads):
+    """The reference's Matcher::getSWResult loop + resultToBuffer (oracle/_ref: ref_align_query, one query per call, one call
+    per host thread) on as many of the same prefilter lists as fit the time budget; also checks the records against the GPU's."""
+    from concurrent.futures import ThreadPoolExecutor
+    from mmseqs2_b200 import alignment as al
+    from oracle.pyoracle import Ref
+    if not Ref.available():
+        return {"unavailable": "oracle/_ref not built"}
+    ref = Ref()
+    to64 = np.ascontiguousarray(toff, np.int64)
+    db_res = int(to64[-1])
+
+    def one(qi):
+        return ref.align_query(queries[qi], qi, tdata, to64, lists[qi], lists[qi], db_res, sw_mode=2, eval_thr=1e-3)
+
+    t0 = time.perf_counter()
+    one(0)
+    per_query = max(1e-4, time.perf_counter() - t0)
+    n = int(min(len(queries), max(threads, budget_s * threads / per_query / 4)))
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        outs = list(ex.map(one, range(n)))
+    dt = time.perf_counter() - t0
+    n_aln = sum(o[1] for o in outs)
+    same = all(al.records(gpu_results[qi], gpu_pool, True, True) == outs[qi][0] for qi in range(n))
+    return {"value": n_aln / dt, "unit": "alignments/s", "cores": threads, "kind": "reference",
+            "sample": "%d of the %d lists (%d alignments) in %.1f s" % (n, len(queries), n_aln, dt), "records_identical_to_gpu": bool(same)}
+
+
 def cpu_reference_sw(queries, td, to, pairs, budget_s, threads):
     """alignScoreEndPos of the reference over a bounded prefix of the pair list, one OpenMP region over queries with one
     SmithWaterman object per thread (the shape of Alignment::run); falls back to the C port when oracle/_ref is absent"""
@@ -505,6 +534,28 @@ def main():
                                                        "ops_per_cell": SW32_OPS_PER_CELL}
                 if not args.no_cpu:
                     sec["cpu_baseline"] = cpu_reference_sw(sq, std, sto, spairs, 10.0, os.cpu_count() or 1)
+                # (c) the whole `align` step for these lists: b200_align_batch (score/end -> E-value + coverage gate -> start -> CIGAR ->
+                #     result assembly, criteria, ordering) and the records of Matcher::resultToBuffer, host buffers end to end
+                try:
+                    from mmseqs2_b200 import alignment as al
+                    order = np.argsort(spairs[:, 0], kind="stable")
+                    bounds = np.searchsorted(spairs[order, 0], np.arange(len(sq) + 1))
+                    lists = [spairs[order[bounds[i]:bounds[i + 1]], 1] for i in range(len(sq))]
+                    evp = al.EvalueParams.defaults("blosum62.out", 11, 1, int(sto[-1]))
+                    apar = al.AlignParams(sw_mode=al.SCORE_COV_SEQID, eval_thr=1e-3)
+                    al.align_batch(ctx, sm, sq[:8], lists[:8], apar, evp)
+                    t0 = time.perf_counter()
+                    ares, apool, n_aln = al.align_batch(ctx, sm, sq, lists, apar, evp)
+                    a_dt = time.perf_counter() - t0
+                    step = {"workload": "`align` step (-a, -e 1e-3) over the same %d prefilter lists: alignments with E-value gate, start "
+                                        "positions and CIGAR for the survivors, criteria, ordering" % len(sq),
+                            "alignments_per_s": n_aln / a_dt, "ms": a_dt * 1e3, "alignments": n_aln,
+                            "accepted": int(sum(len(r) for r in ares)), "unit": "alignments/s", "GCUPS_equivalent": sw_cells / 1e9 / a_dt}
+                    if not args.no_cpu:
+                        step["cpu_baseline"] = cpu_reference_align_step(sq, std, sto, lists, ares, apool, 8.0, os.cpu_count() or 1)
+                    sec["align_step"] = step
+                except Exception as e:  # pragma: no cover
+                    sec["align_step"] = {"error": repr(e)}
                 line.setdefault("secondary", {})["sw_rescoring"] = sec
                 sjob.close()
             except Exception as e:  # pragma: no cover

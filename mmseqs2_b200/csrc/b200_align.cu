@@ -104,13 +104,14 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
                      const uint32_t *__restrict__ order, uint32_t n_seq, int A, uint8_t *__restrict__ out, uint32_t n_queries,
                      uint32_t units_per_query, uint32_t unit_targets, unsigned *__restrict__ unit_counter,
                      uint32_t *__restrict__ tile_bnd, uint32_t bnd_slot_words) {
-    static_assert(K % 4 == 0, "K must be a multiple of 4");
+    static_assert(K % 2 == 0, "K must be even");
     static_assert(!TILED || G == 32, "the tiled (long-query) variant runs one target per warp");
-    constexpr int C = K / 4;
-    constexpr int ROW_U4 = C * G;  // uint4 per residue row
+    constexpr int C = K / 4;           // full uint4 chunks of a lane's K registers ...
+    constexpr int T = (K % 4) / 2;     // ... plus one uint2 tail chunk when K = 4C + 2
+    constexpr int ROW_W = G * K;       // 32-bit words per residue row: [c][g] uint4, then [g] uint2
     extern __shared__ uint4 smem_u4[];
-    uint4 *P = smem_u4;
-    uint4 *Pp = smem_u4 + (size_t) (A + 1) * ROW_U4;
+    uint32_t *P = reinterpret_cast<uint32_t *>(smem_u4);
+    uint32_t *Pp = P + (size_t) (A + 1) * ROW_W;
 
     __shared__ unsigned cur_unit;
     const int lane = threadIdx.x & 31;
@@ -146,12 +147,12 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
         if (TILED) __syncthreads();          // every warp is done with the previous tile's tables (and boundary words)
         const int8_t *prof = raw + q.raw_off;
         const int qlen = q.qlen;
-        uint32_t *Pw = reinterpret_cast<uint32_t *>(P);
-        uint32_t *Ppw = reinterpret_cast<uint32_t *>(Pp);
+        uint32_t *Pw = P;
+        uint32_t *Ppw = Pp;
         const int words = G * K;
         for (int idx = threadIdx.x; idx < (A + 1) * words; idx += blockDim.x) {
             const int a = idx / words, w = idx % words;
-            const int gg = w / K, r = w % K, c = r >> 2, e = r & 3;
+            const int gg = w / K, r = w % K;
             const int r0 = row_base + 2 * w;
             int s0 = 0, s1 = 0, sm1 = 0;  // rows r0, r0+1, r0-1
             if (a < A) {
@@ -160,7 +161,7 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
                 if (r0 + 1 < qlen) s1 = pa[r0 + 1];
                 if (r0 - 1 >= 0 && r0 - 1 < qlen) sm1 = pa[r0 - 1];
             }
-            const int dst = (a * ROW_U4 + c * G + gg) * 4 + e;
+            const int dst = a * ROW_W + (r < 4 * C ? ((r >> 2) * G + gg) * 4 + (r & 3) : 4 * C * G + gg * 2 + (r - 4 * C));
             Pw[dst] = pack16(s0, s1);
             Ppw[dst] = pack16(sm1, s0);
         }
@@ -205,7 +206,8 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
                 const uint32_t a0 = (wv >> (8 * (u & 3))) & 0xffu;
                 const uint32_t a1 = (wv >> (8 * ((u + 1) & 3))) & 0xffu;
                 {   // even column: V from W, same registers
-                    const uint4 *p = P + a0 * ROW_U4 + g;
+                    const uint32_t *prow = P + a0 * ROW_W;
+                    const uint4 *p = reinterpret_cast<const uint4 *>(prow) + g;
 #pragma unroll
                     for (int c = 0; c < C; c++) {
                         const uint4 x = p[c * G];
@@ -214,6 +216,11 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
                         S[4 * c + 2] = __viaddmin_s16x2_relu(S[4 * c + 2], x.z, cst);
                         S[4 * c + 3] = __viaddmin_s16x2_relu(S[4 * c + 3], x.w, cst);
                     }
+                    if (T) {
+                        const uint2 x = reinterpret_cast<const uint2 *>(prow + 4 * C * G)[g];
+                        S[4 * C + 0] = __viaddmin_s16x2_relu(S[4 * C + 0], x.x, cst);
+                        S[4 * C + 1] = __viaddmin_s16x2_relu(S[4 * C + 1], x.y, cst);
+                    }
 #pragma unroll
                     for (int r = 0; r < K; r += 2) best = __vimax3_s16x2(best, S[r], S[r + 1]);
                     if (TILED) bout[u >> 1] = S[K - 1];   // rows (row_base+ROWS-2, row_base+ROWS-1) in the last lane
@@ -221,10 +228,16 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
                 {   // odd column: W from V, shifted by one register
                     uint32_t carry = __shfl_up_sync(0xffffffffu, S[K - 1], 1, G);
                     if (g == 0) carry = TILED ? bin[u >> 1] : 0u;
-                    const uint4 *p = Pp + a1 * ROW_U4 + g;
-                    uint4 x[C];
+                    const uint32_t *prow = Pp + a1 * ROW_W;
+                    const uint4 *p = reinterpret_cast<const uint4 *>(prow) + g;
+                    uint4 x[C > 0 ? C : 1];
 #pragma unroll
                     for (int c = 0; c < C; c++) x[c] = p[c * G];
+                    if (T) {
+                        const uint2 xt = reinterpret_cast<const uint2 *>(prow + 4 * C * G)[g];
+                        S[4 * C + 1] = __viaddmin_s16x2_relu(S[4 * C + 0], xt.y, cst);
+                        S[4 * C + 0] = __viaddmin_s16x2_relu(C > 0 ? S[4 * C - 1] : carry, xt.x, cst);
+                    }
 #pragma unroll
                     for (int c = C - 1; c >= 0; c--) {
                         S[4 * c + 3] = __viaddmin_s16x2_relu(S[4 * c + 2], x[c].w, cst);
@@ -895,11 +908,21 @@ namespace {
 int set_err(b200_ctx *ctx, int code, const char *msg) { return b200_set_err(ctx, code, msg); }
 
 struct ScanCfg { int G, K; };
-const ScanCfg kScanCfgs[] = {{8, 4}, {8, 8}, {8, 12}, {8, 16}, {16, 12}, {16, 16}, {16, 24}, {32, 16}, {32, 24}, {32, 32}};
+// capacity 2*G*K rows, ascending: 32-row steps up to 512 (G=8), 64-row steps up to 1024 (G=16), 128-row steps up to 2048 (G=32)
+#define B200_SCAN_CFGS(X) \
+    X(0, 8, 4) X(1, 8, 6) X(2, 8, 8) X(3, 8, 10) X(4, 8, 12) X(5, 8, 14) \
+    X(6, 8, 16) X(7, 8, 18) X(8, 8, 20) X(9, 8, 22) X(10, 8, 24) X(11, 8, 26) \
+    X(12, 8, 28) X(13, 8, 30) X(14, 8, 32) X(15, 16, 18) X(16, 16, 20) X(17, 16, 22) \
+    X(18, 16, 24) X(19, 16, 26) X(20, 16, 28) X(21, 16, 30) X(22, 16, 32) X(23, 32, 18) \
+    X(24, 32, 20) X(25, 32, 22) X(26, 32, 24) X(27, 32, 26) X(28, 32, 28) X(29, 32, 30) \
+    X(30, 32, 32)
+#define B200_SCAN_ENTRY(n, g, k) {g, k},
+const ScanCfg kScanCfgs[] = {B200_SCAN_CFGS(B200_SCAN_ENTRY)};
+#undef B200_SCAN_ENTRY
 
 template <int G, int K, bool TILED>
 cudaError_t launch_scan_cfg(b200_ctx *ctx, const int8_t *raw, const QueryDesc *qd, int nq, uint8_t *dense) {
-    const size_t smem = (size_t) 2 * (ctx->alphabet + 1) * (K / 4) * G * sizeof(uint4);
+    const size_t smem = (size_t) 2 * (ctx->alphabet + 1) * K * G * sizeof(uint32_t);
     cudaError_t e = cudaFuncSetAttribute(ungapped_scan_kernel<G, K, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -932,24 +955,20 @@ cudaError_t launch_scan_cfg(b200_ctx *ctx, const int8_t *raw, const QueryDesc *q
 // queries of one launch must share a (G,K) configuration; the caller groups them by capacity class
 cudaError_t launch_scan(b200_ctx *ctx, int cfg, const int8_t *raw, const QueryDesc *qd, int nq, uint8_t *dense) {
     switch (cfg) {
-        case 0: return launch_scan_cfg<8, 4, false>(ctx, raw, qd, nq, dense);
-        case 1: return launch_scan_cfg<8, 8, false>(ctx, raw, qd, nq, dense);
-        case 2: return launch_scan_cfg<8, 12, false>(ctx, raw, qd, nq, dense);
-        case 3: return launch_scan_cfg<8, 16, false>(ctx, raw, qd, nq, dense);
-        case 4: return launch_scan_cfg<16, 12, false>(ctx, raw, qd, nq, dense);
-        case 5: return launch_scan_cfg<16, 16, false>(ctx, raw, qd, nq, dense);
-        case 6: return launch_scan_cfg<16, 24, false>(ctx, raw, qd, nq, dense);
-        case 7: return launch_scan_cfg<32, 16, false>(ctx, raw, qd, nq, dense);
-        case 8: return launch_scan_cfg<32, 24, false>(ctx, raw, qd, nq, dense);
-        case 9: return launch_scan_cfg<32, 32, false>(ctx, raw, qd, nq, dense);
+#define B200_SCAN_CASE(n, g, k) case n: return launch_scan_cfg<g, k, false>(ctx, raw, qd, nq, dense);
+        B200_SCAN_CFGS(B200_SCAN_CASE)
+#undef B200_SCAN_CASE
         default: return launch_scan_cfg<32, 32, true>(ctx, raw, qd, nq, dense);   // queries longer than 2047: row tiles of 2048
     }
 }
 
 int scan_cfg_for(int qlen) {
     const int n = (int) (sizeof(kScanCfgs) / sizeof(kScanCfgs[0]));
-    for (int i = 0; i < n; i++)
+    static const bool coarse = getenv("B200_SCAN_COARSE") != nullptr;   // experiments: the round-0 class list only
+    for (int i = 0; i < n; i++) {
+        if (coarse && kScanCfgs[i].K % 4 != 0) continue;     // 64/128/256-row steps only
         if (2 * kScanCfgs[i].G * kScanCfgs[i].K >= qlen + 1) return i;
+    }
     return n;  // tiled long-query variant
 }
 

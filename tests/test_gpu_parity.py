@@ -166,6 +166,29 @@ def test_long_query_tiles_and_gap_variants(ctx, oracle, submat, blosum):
         assert np.array_equal(got, oracle.sw_align(q, cb, bias, td, to, go, ge)), (go, ge)
 
 
+def test_scan_every_capacity_class(ctx, oracle, submat, blosum):
+    """one query at each capacity boundary of the scan kernel's (G,K) classes: qlen = capacity-1 (last row of a class) and
+    qlen = capacity (first length of the next class) for 32-row steps up to 512, 64-row steps up to 1024, 128-row steps beyond"""
+    rng = np.random.default_rng(777)
+    bg = synth.background(blosum[1])
+    caps = list(range(64, 513, 32)) + list(range(576, 1025, 64)) + list(range(1152, 2049, 128))
+    lens = sorted(set([c - 1 for c in caps] + [c for c in caps[:-1]]))
+    res, off = synth.random_seqs(rng, 120, bg, mean=300, sigma=0.8, lo=1, hi=2500)
+    qs = [synth.random_seqs(rng, 1, bg, mean=L, sigma=0, lo=L, hi=L, normal=True)[0] for L in lens]
+    synth.plant_homologs(rng, res, off, qs, bg, frac=0.6, subst=0.15, indel=0.01)
+    seqs = synth.split(res, off)
+    for k in range(0, len(qs), 5):                 # near-identical targets: saturation at 255 - bias in the top rows of a class
+        seqs[k % len(seqs)] = qs[k].copy()
+    td, to = pack_targets(seqs)
+    ctx.load_db(td, to.astype(np.uint64), 21)
+    profs = [submat.ssw_query(q) for q in qs]
+    _, _, dense = ctx.ungapped_scan(profs, want_dense=True)
+    for qi, q in enumerate(qs):
+        cb, bias = oracle.query_cb(q, True)
+        exp = oracle.ungapped(q, cb, bias, td, to)
+        assert np.array_equal(dense[qi].astype(np.int32), exp), (len(q), np.nonzero(dense[qi] != exp)[0][:5])
+
+
 def test_scan_long_queries_tiled(ctx, oracle, submat, blosum):
     """queries beyond one 2048-row tile (2048, 2049, 4095, 4096, 5000 rows) and a 1-residue query"""
     rng = np.random.default_rng(2048)
