@@ -97,8 +97,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 // P / P' are the two packings of the int16 query profile, staged in shared memory, laid out [a][c][g] as uint4 so
 // that a group's LDS.128 is conflict-free.
 // ------------------------------------------------------------------------------------------------
+#ifndef B200_SCAN_MINB
+#define B200_SCAN_MINB 3
+#endif
 template <int G, int K, bool TILED>
-__global__ void __launch_bounds__(256, (K <= 12 && !TILED) ? 5 : 1)
+__global__ void __launch_bounds__(256, TILED ? 1 : (K <= 12 ? 5 : (K <= 24 ? B200_SCAN_MINB : 1)))
 ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict__ qd, const uint8_t *__restrict__ db,
                      const uint64_t *__restrict__ off, const int32_t *__restrict__ len,
                      const uint32_t *__restrict__ order, uint32_t n_seq, int A, uint8_t *__restrict__ out, uint32_t n_queries,
