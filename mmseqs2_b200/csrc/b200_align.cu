@@ -24,10 +24,11 @@ struct QueryDesc {     // device-side description of one query profile
     uint64_t raw_off;  // byte offset of the raw [A][qlen] int8 profile in d_raw
     uint64_t pad_off;  // byte offset of the padded [(A+1)][Lp] profile in d_pad (forward; reversed copy follows at +rev_off)
     uint64_t rev_off;
+    uint64_t p16_off;  // forward copy for the packed kernel: rows of the last (partial) tile at a lane stride rounded up to 4
     int32_t qlen;
     int32_t Lp;
     int32_t bias;
-    int32_t pad_;
+    int32_t k16;       // rows per lane of the packed kernel's last tile (even, 2..16)
 };
 
 struct PairDesc {  // one (query,target) work unit of the gapped kernel, device side
@@ -404,13 +405,24 @@ __global__ void pad_profile_kernel(const int8_t *__restrict__ raw, const QueryDe
     const int8_t *src = raw + q.raw_off;
     int8_t *fwd = padded + q.pad_off;
     int8_t *rev = padded + q.rev_off;
+    int8_t *p16 = padded + q.p16_off;
     const int total = (A + 1) * q.Lp;
+    // packed-kernel copy: full 512-row tiles as they are; in the last tile lane l owns rows [l*k16, (l+1)*k16) stored at
+    // byte l*kp (kp = k16 rounded up to 4), so that its vector load stays aligned for k16 = 2, 6, 10, 14
+    const int last_base = (q.qlen - 1) / 512 * 512, kp = (q.k16 + 3) / 4 * 4;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
         const int a = idx / q.Lp, j = idx % q.Lp;
-        int8_t f = -128, r = -128;
+        int8_t f = -128, r = -128, s16 = -128;
         if (a < A && j < q.qlen) { f = src[(size_t) a * q.qlen + j]; r = src[(size_t) a * q.qlen + (q.qlen - 1 - j)]; }
+        int row = j;
+        if (j >= last_base) {
+            const int jl = j - last_base, ln = jl / kp, e = jl % kp;
+            row = (ln < 32 && e < q.k16) ? last_base + ln * q.k16 + e : q.qlen;
+        }
+        if (a < A && row < q.qlen) s16 = src[(size_t) a * q.qlen + row];
         fwd[idx] = f;
         rev[idx] = r;
+        p16[idx] = s16;
     }
 }
 
@@ -605,8 +617,9 @@ __device__ __forceinline__ uint32_t sw16_tile(const int8_t *pptr, int Lp, const 
                                               const uint2 *bnd_rd, uint2 *bnd_wr, bool write_bnd, uint32_t best,
                                               uint32_t target = 0, int row_base = 0, uint32_t *key_lo = nullptr,
                                               uint32_t *key_hi = nullptr, const int8_t *pptr_b = nullptr, uint32_t rev_shift = 0) {
-    static_assert(K % 4 == 0 && K <= 16, "K in {4,8,12,16}");
-    constexpr int W = K / 4;
+    static_assert(K % 2 == 0 && K <= 16 && (!REV || K % 4 == 0), "K even, <= 16 (multiple of 4 in the reverse pass)");
+    constexpr int KP = (K + 3) / 4 * 4;   // bytes a lane owns in the profile row (K = 2, 6, 10, 14 leave two unused)
+    constexpr int W = KP / 4;
     constexpr int TDIR = REV ? -1 : 1;
     const int lane = threadIdx.x & 31;
     const uint32_t padres = (uint32_t) A | ((uint32_t) A << 8);
@@ -666,11 +679,11 @@ __device__ __forceinline__ uint32_t sw16_tile(const int8_t *pptr, int Lp, const 
                 wa[w] = reinterpret_cast<const uint32_t *>(ppa)[w];
                 wb[w] = reinterpret_cast<const uint32_t *>(ppb)[w];
             }
-        } else if constexpr (K == 16) {
+        } else if constexpr (KP == 16) {
             const uint4 va = *reinterpret_cast<const uint4 *>(ppa), vb = *reinterpret_cast<const uint4 *>(ppb);
             wa[0] = va.x; wa[1] = va.y; wa[2] = va.z; wa[3] = va.w;
             wb[0] = vb.x; wb[1] = vb.y; wb[2] = vb.z; wb[3] = vb.w;
-        } else if constexpr (K == 8) {
+        } else if constexpr (KP == 8) {
             const uint2 va = *reinterpret_cast<const uint2 *>(ppa), vb = *reinterpret_cast<const uint2 *>(ppb);
             wa[0] = va.x; wa[1] = va.y; wb[0] = vb.x; wb[1] = vb.y;
         } else {
@@ -820,14 +833,27 @@ __device__ __forceinline__ void sw16_item(const int8_t *prof_base, const QueryDe
             const int kk = last ? k_last : 16;
             // REV: a half whose rectangle has fewer rows than its partner's keeps reading, so clamp into the pad columns
             // at the end of the profile row (everything beyond the half's own rows must read as pad anyway)
-            const int8_t *pl = prof_base + min(offa + tile * 512 + lane * kk, Lp - 16);
-            const int8_t *plb = prof_base + min(offb + tile * 512 + lane * kk, Lp - 16);
-            switch (kk) {
-                case 4: best = sw16_tile_any<4, FIND, REV>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi, plb, rev_shift); break;
-                case 8: best = sw16_tile_any<8, FIND, REV>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi, plb, rev_shift); break;
-                case 12: best = sw16_tile_any<12, FIND, REV>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi, plb, rev_shift); break;
-                default: best = sw16_tile_any<16, FIND, REV>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi, plb, rev_shift); break;
+            const int kp = (kk + 3) & ~3;
+            const int8_t *pl = prof_base + min(offa + tile * 512 + lane * kp, Lp - 16);
+            const int8_t *plb = prof_base + min(offb + tile * 512 + lane * kp, Lp - 16);
+#define B200_SW16_TILE(KK) best = sw16_tile_any<KK, FIND, REV>(tile == 0, pl, Lp, pa_t, pb_t, tla, tlb, ncols, A, neg_ge2, neg_go2, bnd_rd, \
+                                                              bnd_wr, !last, best, target, tile * 512, &key_lo, &key_hi, plb, rev_shift)
+            if (REV || (kk & 3) == 0) {
+                switch (kk) {
+                    case 4: B200_SW16_TILE(4); break;
+                    case 8: B200_SW16_TILE(8); break;
+                    case 12: B200_SW16_TILE(12); break;
+                    default: B200_SW16_TILE(16); break;
+                }
+            } else if constexpr (!REV) {
+                switch (kk) {
+                    case 2: B200_SW16_TILE(2); break;
+                    case 6: B200_SW16_TILE(6); break;
+                    case 10: B200_SW16_TILE(10); break;
+                    default: B200_SW16_TILE(14); break;
+                }
             }
+#undef B200_SW16_TILE
             if (FIND) {   // earliest (column, row) so far per half; later tiles only need the columns up to it
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
@@ -884,7 +910,7 @@ sw16_kernel(const int8_t *__restrict__ padded, const QueryDesc *__restrict__ qd,
         if (item_idx >= n_items) break;
         const WorkItem item = items[item_idx];
         const QueryDesc q = qd[item.query];
-        const int8_t *gprof = padded + (MODE == 2 ? q.rev_off : q.pad_off);
+        const int8_t *gprof = padded + (MODE == 2 ? q.rev_off : q.p16_off);
         if (threadIdx.x == 0) next_pair = item.p0;
         if (SMEM) {
             const unsigned bytes = (unsigned) ((A + 1) * q.Lp);
@@ -975,6 +1001,12 @@ int scan_cfg_for(int qlen) {
     return n;  // tiled long-query variant
 }
 
+// rows per lane (2,4,...,16) of the LAST tile of the packed kernel for a query length; every earlier tile is 512 rows
+int sw16_k_for(int qlen) {
+    const int rem = qlen - (qlen - 1) / 512 * 512;  // 1..512 rows left for the last tile
+    return std::min(16, (rem + 63) / 64 * 2);
+}
+
 // stage raw profiles + descriptors for a set of queries; fills h_qd (pad offsets only when with_pad)
 int stage_queries(b200_ctx *ctx, const b200_query *queries, int nq, bool with_pad, std::vector<QueryDesc> &h_qd) {
     const int A = ctx->alphabet;
@@ -990,8 +1022,9 @@ int stage_queries(b200_ctx *ctx, const b200_query *queries, int nq, bool with_pa
         d.Lp = (int) round_up((uint64_t) d.qlen, 128) + 512;
         d.pad_off = pad_bytes;
         d.rev_off = pad_bytes + (uint64_t) (A + 1) * d.Lp;
-        pad_bytes += 2 * (uint64_t) (A + 1) * d.Lp;
-        d.pad_ = 0;
+        d.p16_off = pad_bytes + 2 * (uint64_t) (A + 1) * d.Lp;
+        pad_bytes += 3 * (uint64_t) (A + 1) * d.Lp;
+        d.k16 = sw16_k_for(d.qlen);
     }
     std::vector<int8_t> h_raw(raw_bytes, 0);
     for (int i = 0; i < nq; i++) memcpy(h_raw.data() + h_qd[i].raw_off, queries[i].profile, (size_t) A * h_qd[i].qlen);
@@ -1344,14 +1377,6 @@ int b200_diag_score(b200_ctx *ctx, const b200_query *q, const uint32_t *ids, con
 namespace {
 
 constexpr uint32_t kPairsPerItem = 8;
-
-// rows per lane (4/8/12/16) of the LAST tile of the packed kernel for a query length; every earlier tile is 512 rows
-int sw16_k_for(int qlen) {
-    const int rem = qlen - (qlen - 1) / 512 * 512;  // 1..512 rows left for the last tile
-    return std::min(16, ((rem + 31) / 32 + 3) / 4 * 4);
-}
-
-
 
 struct SwPlan {
     std::vector<uint32_t> perm;  // sorted position -> caller index
@@ -1731,7 +1756,7 @@ int b200_sw_job_create(b200_ctx *ctx, const b200_query *queries, int nq, const b
     job->n_items = (uint32_t) plan.items.size();
     job->bnd_stride = multi ? (int) round_up((uint64_t) max_cols, 32) + 32 : 32;
     job->smem_bytes = max_Lp;
-    const size_t pad_bytes = h_qd.back().rev_off + (size_t) (ctx->alphabet + 1) * h_qd.back().Lp;
+    const size_t pad_bytes = h_qd.back().p16_off + (size_t) (ctx->alphabet + 1) * h_qd.back().Lp;
     cudaError_t e = job->pad.reserve(pad_bytes);
     if (e == cudaSuccess) e = job->qdesc.reserve(sizeof(QueryDesc) * nq);
     if (e == cudaSuccess) e = job->pairs.reserve(sizeof(PairDesc) * n);
@@ -1987,7 +2012,7 @@ int b200_sw_score_job_create(b200_ctx *ctx, const b200_query *queries, int nq, c
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     }
     job->bnd_stride = multi ? (int) round_up((uint64_t) max_cols, 32) + 32 : 32;
-    const size_t pad_bytes = h_qd.back().rev_off + (size_t) (A + 1) * h_qd.back().Lp;
+    const size_t pad_bytes = h_qd.back().p16_off + (size_t) (A + 1) * h_qd.back().Lp;
     if (e == cudaSuccess) e = job->pad.reserve(pad_bytes);
     if (e == cudaSuccess) e = job->qdesc.reserve(sizeof(QueryDesc) * nq);
     if (e == cudaSuccess) e = job->bnd.reserve(sizeof(int2) * 2 * (size_t) job->bnd_stride * std::min<uint64_t>(max_items, sw_max_grid(ctx)) * 8);
