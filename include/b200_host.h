@@ -8,6 +8,8 @@
  *   b200h_ssw_bias         profile bias constant                           src/alignment/StripedSmithWaterman.cpp:1375-1406
  *   b200h_build_profile    profile_word_linear / createProfile contents    StripedSmithWaterman.cpp:1434-1439,
  *                                                                          UngappedAlignment.cpp:412-420
+ *   b200h_build_profile_pssm  the HMM_PROFILE branches of both             StripedSmithWaterman.cpp:1388-1406,
+ *                                                                          UngappedAlignment.cpp:405-411
  */
 #ifndef B200_HOST_H
 #define B200_HOST_H
@@ -24,6 +26,11 @@ int b200h_ssw_bias(const int16_t *mat, int A, const int8_t *cb, int L, int cb_en
 /* out[a*L + j] = (target_major ? mat[a][q[j]] : mat[q[j]][a]) + cb[j]; returns 0, or -4 (B200_ERR_RANGE) if a value
  * leaves int8.  target_major=1 is the gapped / scan profile, 0 the per-diagonal scorer's. */
 int b200h_build_profile(const int16_t *mat, int A, const uint8_t *q, int L, const int8_t *cb, int target_major, int8_t *out);
+/* Profile (PSSM) query: pssm = Sequence::getAlignmentProfile(), [rows][L] int8 with rows = Sequence::PROFILE_AA_SIZE (20).
+ * out[A][L]: the first `rows` residue rows copied, the remaining ones (X: "neutral state", score 0) zero -- the layout every
+ * device entry point takes (per-diagonal scorer included: its [pos][A+... ] table holds the same values).  Returns the SSW
+ * profile bias |min(0, min pssm)| (no composition bias in the profile branch), or -1 (B200_ERR_ARG) on bad sizes. */
+int b200h_build_profile_pssm(const int8_t *pssm, int rows, int L, int A, int8_t *out);
 
 #ifdef __cplusplus
 }

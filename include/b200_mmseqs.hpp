@@ -139,6 +139,14 @@ public:
         return b200h_build_profile(mat_.data(), A_, numSequence, L, cb_.data(), /*target_major=*/0, profile_.data());
     }
 
+    // createProfile for a Sequence of type HMM_PROFILE (UngappedAlignment.cpp:405-411): alignmentProfile =
+    // seq->getAlignmentProfile(), [PROFILE_AA_SIZE][L] int8; no bias correction in this branch
+    int createProfile(const int8_t *alignmentProfile, int profileRows, int L) {
+        qlen_ = L;
+        profile_.resize((size_t) A_ * L);
+        return b200h_build_profile_pssm(alignmentProfile, profileRows, L, A_, profile_.data()) < 0 ? B200_ERR_ARG : B200_OK;
+    }
+
     // align(CounterResult*, n)   UngappedAlignment.cpp:36-42 -- counts updated in place
     int align(CounterResult *results, size_t n) { return run(results, n, NULL); }
 
@@ -196,6 +204,18 @@ public:
         profile_.resize((size_t) A_ * L);
         targets_.clear();
         return b200h_build_profile(mat_.data(), A_, numSequence, L, cb_.data(), /*target_major=*/1, profile_.data());
+    }
+
+    // ssw_init for a profile query (the isProfile branch, StripedSmithWaterman.cpp:1388-1425): consensus = q->numSequence
+    // (identity counting in the backtrace), alignmentProfile = q->getAlignmentProfile(), [PROFILE_AA_SIZE][L] int8
+    int ssw_init(const unsigned char *consensus, const int8_t *alignmentProfile, int profileRows, int L) {
+        qlen_ = L;
+        seq_.assign(consensus, consensus + L);
+        cb_.assign(L, 0);
+        profile_.resize((size_t) A_ * L);
+        targets_.clear();
+        bias_ = b200h_build_profile_pssm(alignmentProfile, profileRows, L, A_, profile_.data());
+        return bias_ < 0 ? B200_ERR_ARG : B200_OK;
     }
 
     void addTarget(uint32_t dbId) { targets_.push_back(dbId); }

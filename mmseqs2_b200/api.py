@@ -111,6 +111,18 @@ class SubMatrix:
             raise B200Error("profile value outside int8")
         return QueryProfile(prof, bias, cb)
 
+    def pssm_query(self, pssm):
+        """Profile (PSSM) query, the HMM_PROFILE branch of ssw_init / createProfile: pssm = int8 [20][L] as
+        Sequence::getAlignmentProfile() holds it.  The same [A][L] table serves the scan, the gapped kernels and the
+        per-diagonal scorer."""
+        pssm = np.ascontiguousarray(pssm, np.int8)
+        rows, L = pssm.shape
+        prof = np.zeros((self.A, L), np.int8)
+        bias = self.lib.b200h_build_profile_pssm(_p(pssm), rows, L, self.A, _p(prof))
+        if bias < 0:
+            raise B200Error("bad PSSM shape")
+        return QueryProfile(prof, bias, np.zeros(L, np.int8))
+
     def diag_query(self, q, bias_f32=None):
         """UngappedAlignment::createProfile: profile[a][j] = mat[q[j]][a] + round(bias[j]/4)."""
         q = np.ascontiguousarray(q, np.uint8)

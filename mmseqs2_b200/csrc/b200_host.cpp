@@ -60,4 +60,17 @@ int b200h_build_profile(const int16_t *mat, int A, const uint8_t *q, int L, cons
     return rc;
 }
 
+// HMM_PROFILE branch of ssw_init (StripedSmithWaterman.cpp:1388-1406): profile->mat = the alignment profile with the X row
+// cleared; bias = |smallest entry of the caller's [rows][L] table| (abs(compositionBias) is 0 here).
+int b200h_build_profile_pssm(const int8_t *pssm, int rows, int L, int A, int8_t *out) {
+    if (pssm == nullptr || out == nullptr || rows <= 0 || rows > A || L <= 0) return -1;
+    int lowest = 0;
+    for (size_t i = 0; i < (size_t) rows * L; i++) {
+        out[i] = pssm[i];
+        if (pssm[i] < lowest) lowest = pssm[i];
+    }
+    for (size_t i = (size_t) rows * L; i < (size_t) A * L; i++) out[i] = 0;
+    return lowest < 0 ? -lowest : lowest;
+}
+
 }  // extern "C"

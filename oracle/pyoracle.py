@@ -218,6 +218,35 @@ class Ref:
         n = self.lib.ref_prefilter_roundtrip(entry + b"\0", _p(ids), _p(sc), _p(dg), ctypes.c_int64(cap), out)
         return ids[:n], sc[:n], dg[:n], out.value
 
+    # ---- profile (PSSM) queries (ref_glue.cpp: ref_profile_align / ref_profile_diag) ----
+    def profile_align(self, pssm, consensus, tdata, toff, mode=1, go=11, ge=1, eval_thr=1e9, cov_mode=0, cov_thr=0.0, db_residues=None,
+                      want_bt=False):
+        """pssm: int8 [20][L] (Sequence::getAlignmentProfile layout).  mode -1: ungapped scores only.  -> (out[n][10], evalues, bts)"""
+        pssm = np.ascontiguousarray(pssm, np.int8)
+        cons = np.ascontiguousarray(consensus, np.uint8)
+        to = np.ascontiguousarray(toff, np.int64)
+        n = len(to) - 1
+        out = np.zeros((n, 10), np.int32)
+        ev = np.zeros(n, np.float64)
+        stride = int(np.diff(to).max()) + pssm.shape[1] + 8 if want_bt else 0
+        bt = ctypes.create_string_buffer(max(1, stride * n)) if want_bt else None
+        self.lib.ref_profile_align(_p(pssm), _p(cons), pssm.shape[1], _p(tdata), _p(to), ctypes.c_int64(n), go, ge, mode,
+                                   ctypes.c_double(eval_thr), cov_mode, ctypes.c_float(cov_thr),
+                                   ctypes.c_int64(int(to[-1]) if db_residues is None else db_residues), _p(out), _p(ev), bt,
+                                   ctypes.c_int64(stride))
+        bts = [bt.raw[i * stride:(i + 1) * stride].split(b"\0", 1)[0] for i in range(n)] if want_bt else None
+        return out, ev, bts
+
+    def profile_diag(self, pssm, consensus, tdata, toff, ids, diags):
+        pssm = np.ascontiguousarray(pssm, np.int8)
+        cons = np.ascontiguousarray(consensus, np.uint8)
+        to = np.ascontiguousarray(toff, np.int64)
+        ids = np.ascontiguousarray(ids, np.uint32); dg = np.ascontiguousarray(diags, np.uint16)
+        counts = np.zeros(len(ids), np.uint8); raw = np.zeros(len(ids), np.int32)
+        self.lib.ref_profile_diag(_p(pssm), _p(cons), pssm.shape[1], _p(tdata), _p(to), ctypes.c_int64(len(to) - 1), _p(ids), _p(dg),
+                                  ctypes.c_int64(len(ids)), _p(counts), _p(raw))
+        return counts, raw
+
     def bit_score(self, go, ge, db_residues, score):
         b = ctypes.c_double(0)
         self.lib.ref_evalue(go, ge, ctypes.c_int64(db_residues), ctypes.c_double(score), ctypes.c_double(100.0), ctypes.byref(b))

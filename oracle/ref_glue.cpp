@@ -64,7 +64,9 @@ void block_free_pos_bias(PosBias *p) { free(p); }
 AAMatrix *block_new_simple_aamatrix(int8_t, int8_t) { return (AAMatrix *) blob(); }
 void block_free_aamatrix(AAMatrix *m) { free(m); }
 void block_set_aamatrix_num(AAMatrix *, int8_t, int8_t, int8_t) {}
-AAProfile *block_new_aaprofile(size_t, size_t, int8_t) { return (AAProfile *) blob(); }
+// the profile branch of alignStartPosBacktraceBlock fills the object's position/residue tables itself
+// (StripedSmithWaterman.cpp:964-992): (len+1)*32 bytes and (len+1) int16 with the stand-in's row length of 0
+AAProfile *block_new_aaprofile(size_t len, size_t, int8_t) { return (AAProfile *) calloc(1, (len + 2) * 64 + 4096); }
 void block_free_aaprofile(AAProfile *p) { free(p); }
 size_t block_get_curr_len_aaprofile(const AAProfile *) { return 0; }
 void block_set_all_gap_open_C_aaprofile(AAProfile *, int8_t) {}
@@ -491,6 +493,79 @@ int64_t ref_prefilter_roundtrip(const char *entry, uint32_t *ids, int32_t *score
     }
     *p = '\0';
     return (int64_t) hits.size();
+}
+
+// ---- profile (PSSM) queries: the HMM_PROFILE branches of ssw_init (StripedSmithWaterman.cpp:1388-1425)
+// and UngappedAlignment::createProfile (UngappedAlignment.cpp:405-411), fed through a Sequence of type HMM_PROFILE whose
+// alignment profile ([PROFILE_AA_SIZE][L] int8, what Sequence::mapProfile leaves in profile_for_alignment, Sequence.cpp:334-339)
+// and consensus (numSequence) are set directly.
+namespace {
+Sequence *makeProfileSeq(size_t maxLen, const int8_t *pssm, const unsigned char *consensus, int L) {
+    Sequence *s = new Sequence(maxLen, Parameters::DBTYPE_HMM_PROFILE, g_aa, 0, false, false);
+    s->L = L;
+    memcpy(s->numSequence, consensus, L);
+    memset(s->profile_for_alignment, 0, (size_t) L * g_aa->alphabetSize);
+    memcpy(s->profile_for_alignment, pssm, (size_t) L * Sequence::PROFILE_AA_SIZE);
+    return s;
+}
+}  // namespace
+
+// mode < 0: ungapped_alignment only (out[i*10] = score).  Otherwise as ref_ssw_align (same out layout).
+void ref_profile_align(const int8_t *pssm, const unsigned char *consensus, int qL, const unsigned char *tdata, const int64_t *toff,
+                       int64_t n, int gapOpen, int gapExtend, int mode, double evalThr, int covMode, float covThr, int64_t dbResidues,
+                       int32_t *out, double *evalues, char *bt, int64_t btStride) {
+    size_t maxLen = qL;
+    for (int64_t i = 0; i < n; i++) maxLen = std::max(maxLen, (size_t) (toff[i + 1] - toff[i]));
+    maxLen += 64;
+    EvalueComputation evaluer((size_t) dbResidues, g_aa, 11, 1);
+    SmithWaterman sw(maxLen, g_aa->alphabetSize, false, 1.0f, g_aa);
+    Sequence *q = makeProfileSeq(maxLen, pssm, consensus, qL);
+    sw.ssw_init(q, q->getAlignmentProfile(), g_aa);
+    std::string backtrace;
+    for (int64_t i = 0; i < n; i++) {
+        int32_t *o = out + i * 10;
+        const unsigned char *t = tdata + toff[i];
+        const int32_t tL = (int32_t) (toff[i + 1] - toff[i]);
+        if (mode < 0) { o[0] = sw.ungapped_alignment(t, tL); continue; }
+        backtrace.clear();
+        s_align r;
+        memset(&r, 0, sizeof(r));
+        r = sw.ssw_align(t, tL, backtrace, (uint8_t) gapOpen, (uint8_t) gapExtend, (uint8_t) mode, evalThr, &evaluer, covMode, covThr,
+                         0.0f, qL / 2);
+        o[0] = (int32_t) r.score1; o[1] = r.qStartPos1; o[2] = r.qEndPos1; o[3] = r.dbStartPos1; o[4] = r.dbEndPos1;
+        o[5] = r.word; o[6] = (int32_t) r.identicalAACnt; o[7] = (int32_t) backtrace.size();
+        o[8] = (int32_t) (r.qCov * 1e6f + 0.5f); o[9] = (int32_t) (r.tCov * 1e6f + 0.5f);
+        if (evalues != NULL) evalues[i] = r.evalue;
+        if (bt != NULL) {
+            size_t len = std::min((size_t) btStride - 1, backtrace.size());
+            memcpy(bt + i * btStride, backtrace.data(), len);
+            bt[i * btStride + len] = '\0';
+        }
+        if (r.cigar != NULL) { delete[] r.cigar; }
+    }
+    delete q;
+}
+
+// per-diagonal scorer with a profile query (as ref_diag_align)
+void ref_profile_diag(const int8_t *pssm, const unsigned char *consensus, int qL, const unsigned char *tdata, const int64_t *toff,
+                      int64_t nT, const uint32_t *hitIds, const uint16_t *hitDiags, int64_t nHits, uint8_t *counts, int32_t *rescored) {
+    size_t maxLen = qL;
+    for (int64_t i = 0; i < nT; i++) maxLen = std::max(maxLen, (size_t) (toff[i + 1] - toff[i]));
+    maxLen += 64;
+    SequenceLookup lookup((size_t) nT, (size_t) toff[nT]);
+    for (int64_t i = 0; i < nT; i++)
+        lookup.addSequence((unsigned char *) (tdata + toff[i]), (int) (toff[i + 1] - toff[i]), (size_t) i, (size_t) toff[i]);
+    Sequence *q = makeProfileSeq(maxLen, pssm, consensus, qL);
+    UngappedAlignment ua((unsigned int) maxLen, g_aa, &lookup);
+    ua.createProfile(q, NULL);
+    std::vector<CounterResult> hits((size_t) nHits);
+    for (int64_t i = 0; i < nHits; i++) { hits[i].id = hitIds[i]; hits[i].diagonal = hitDiags[i]; hits[i].count = 0; }
+    ua.align(hits.data(), (size_t) nHits);
+    for (int64_t i = 0; i < nHits; i++) {
+        counts[i] = hits[i].count;
+        if (rescored != NULL) rescored[i] = ua.scoreSingelSequenceByCounterResult(hits[i]);
+    }
+    delete q;
 }
 
 }  // extern "C"
