@@ -114,6 +114,20 @@ int b200_align_batch(b200_ctx *ctx, const int16_t *sub_matrix, const double *p_b
                      const uint32_t *target_keys, const b200_align_params *params, const b200_evalue_params *evalue,
                      b200_result *results, uint32_t *n_results, char *bt_pool, uint64_t bt_cap, uint64_t *n_alignments);
 
+/* The same loop for nucleotide searches: Matcher::getSWResult takes the BandedNucleotideAligner branch (Matcher.cpp:72-78),
+ * alignmentMode is forced to SCORE_COV_SEQID, and every hit carries its prefilter diagonal and strand.
+ *   hit_diagonals[n_hits]   (short) hit_t::diagonal of the prefilter record
+ *   hit_reverse[n_hits]     may be NULL; non-zero = reverse-strand hit (reversePrefilterResult && prefScore < 0, Alignment.cpp:360):
+ *                           the read is reverse-complemented (BandedNucleotideAligner::initQuery, :60-66) and the result carries
+ *                           dbStartPos/dbEndPos swapped as Matcher.cpp:131 does
+ * The DB must be loaded with alphabet 5; params->gap_open/gap_extend are 5/2 by default in the reference, params->sw_mode and
+ * comp_bias are ignored; zdrop = par.zdrop (40).  Not covered: wrapped scoring. */
+int b200_align_batch_nucl(b200_ctx *ctx, const uint8_t *query_residues, const uint64_t *query_offsets, const uint32_t *query_keys,
+                          uint32_t n_queries, const uint64_t *hit_offsets, const uint32_t *hit_targets,
+                          const int16_t *hit_diagonals, const uint8_t *hit_reverse, const uint32_t *target_keys,
+                          const b200_align_params *params, int zdrop, const b200_evalue_params *evalue, b200_result *results,
+                          uint32_t *n_results, char *bt_pool, uint64_t bt_cap, uint64_t *n_alignments);
+
 #ifdef __cplusplus
 }
 #endif

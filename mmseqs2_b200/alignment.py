@@ -131,6 +131,36 @@ def align_batch(ctx, submat, queries, hit_lists, params, evalue, query_keys=None
     return out, pool.raw, int(n_aln.value)
 
 
+def align_batch_nucl(ctx, reads, hit_lists, hit_diagonals, hit_reverse, params, evalue, zdrop=40, query_keys=None, target_keys=None):
+    """Alignment::run for a nucleotide search batch.  reads: list of numeric uint8 arrays (A,C,T,G,X = 0..4); per read the
+    DB-local target ids, prefilter diagonals (int16) and strand flags (or None) in list order."""
+    lib = load_library()
+    nq = len(reads)
+    qoff = np.zeros(nq + 1, np.uint64)
+    qoff[1:] = np.cumsum([len(q) for q in reads])
+    qres = np.concatenate([np.ascontiguousarray(q, np.uint8) for q in reads]) if nq else np.zeros(0, np.uint8)
+    hoff = np.zeros(nq + 1, np.uint64)
+    hoff[1:] = np.cumsum([len(h) for h in hit_lists])
+    n_hits = int(hoff[-1])
+    cat = lambda xs, dt: np.ascontiguousarray(np.concatenate([np.asarray(x, dt) for x in xs]) if n_hits else np.zeros(0, dt), dt)  # noqa: E731
+    htg = cat(hit_lists, np.uint32)
+    hdg = cat(hit_diagonals, np.int16)
+    hrv = None if hit_reverse is None else cat(hit_reverse, np.uint8)
+    qk = None if query_keys is None else np.ascontiguousarray(query_keys, np.uint32)
+    tk = None if target_keys is None else np.ascontiguousarray(target_keys, np.uint32)
+    res = np.zeros(max(1, n_hits), RESULT_DTYPE)
+    nres = np.zeros(max(1, nq), np.uint32)
+    n_aln = ctypes.c_uint64(0)
+    bt_cap = 16 + sum((2 * len(reads[i]) + 72) * len(hit_lists[i]) for i in range(nq))
+    pool = ctypes.create_string_buffer(bt_cap)
+    rc = lib.b200_align_batch_nucl(ctx.h, _p(qres), _p(qoff), _p(qk), ctypes.c_uint32(nq), _p(hoff), _p(htg), _p(hdg), _p(hrv), _p(tk),
+                                   ctypes.byref(params), int(zdrop), ctypes.byref(evalue), _p(res), _p(nres), pool, _u64(bt_cap),
+                                   ctypes.byref(n_aln))
+    ctx._check(rc)
+    out = [res[int(hoff[i]):int(hoff[i]) + int(nres[i])].copy() for i in range(nq)]
+    return out, pool.raw, int(n_aln.value)
+
+
 def records(results, pool, add_backtrace=True, compress=True):
     """The alignment DB entry of one query (what Alignment::run writes for it, Alignment.cpp:505-512)."""
     parts = []

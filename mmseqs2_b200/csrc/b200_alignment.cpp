@@ -510,3 +510,144 @@ int b200_align_batch(b200_ctx *ctx, const int16_t *sub_matrix, const double *p_b
     if (n_alignments != nullptr) *n_alignments = n_aln;
     return B200_OK;
 }
+
+// ---- nucleotide searches: the BandedNucleotideAligner branch of getSWResult ---------------------------------------------------
+int b200_align_batch_nucl(b200_ctx *ctx, const uint8_t *query_residues, const uint64_t *query_offsets, const uint32_t *query_keys,
+                          uint32_t n_queries, const uint64_t *hit_offsets, const uint32_t *hit_targets,
+                          const int16_t *hit_diagonals, const uint8_t *hit_reverse, const uint32_t *target_keys,
+                          const b200_align_params *params, int zdrop, const b200_evalue_params *evalue, b200_result *results,
+                          uint32_t *n_results, char *bt_pool, uint64_t bt_cap, uint64_t *n_alignments) {
+    if (ctx == nullptr) return B200_ERR_ARG;
+    if (query_residues == nullptr || query_offsets == nullptr || hit_offsets == nullptr || params == nullptr || evalue == nullptr ||
+        n_results == nullptr)
+        return b200_set_err(ctx, B200_ERR_ARG, "b200_align_batch_nucl: NULL argument");
+    const uint64_t n_hits = hit_offsets[n_queries];
+    if (n_hits > 0 && (hit_targets == nullptr || hit_diagonals == nullptr || results == nullptr))
+        return b200_set_err(ctx, B200_ERR_ARG, "b200_align_batch_nucl: NULL hit list / result array");
+    const uint64_t n_db = b200_db_num_seqs(ctx);
+    if (n_db == 0) return b200_set_err(ctx, B200_ERR_NODB, "no target DB loaded");
+    if (ctx->alphabet != 5) return b200_set_err(ctx, B200_ERR_ARG, "b200_align_batch_nucl: the DB must be loaded with alphabet 5");
+    for (uint64_t k = 0; k < n_hits; k++)
+        if (hit_targets[k] >= n_db) return b200_set_err(ctx, B200_ERR_ARG, "b200_align_batch_nucl: target id out of range");
+    const int32_t *db_len = ctx->h_len.data();
+
+    // reads as given, followed by the reverse complements of the reads that have reverse-strand hits
+    // (NucleotideMatrix::reverseResidue, NucleotideMatrix.cpp:9-13: A<->T, C<->G, X stays; codes A,C,T,G,X = 0..4)
+    static const uint8_t kComplement[5] = {2, 3, 0, 1, 4};
+    std::vector<uint8_t> reads(query_residues, query_residues + query_offsets[n_queries]);
+    std::vector<uint64_t> roff(query_offsets, query_offsets + n_queries + 1);
+    std::vector<uint32_t> rc_index(n_queries, UINT32_MAX);
+    for (uint32_t qi = 0; qi < n_queries; qi++) {
+        const uint64_t L = query_offsets[qi + 1] - query_offsets[qi];
+        if (L > 32767) return b200_set_err(ctx, B200_ERR_RANGE, "b200_align_batch_nucl: read longer than 32767");
+        for (uint64_t j = 0; j < L; j++)
+            if (query_residues[query_offsets[qi] + j] > 4) return b200_set_err(ctx, B200_ERR_ARG, "b200_align_batch_nucl: residue code > 4");
+        bool any_rev = false;
+        if (hit_reverse != nullptr)
+            for (uint64_t k = hit_offsets[qi]; k < hit_offsets[qi + 1] && !any_rev; k++) any_rev = hit_reverse[k] != 0;
+        if (!any_rev) continue;
+        rc_index[qi] = (uint32_t) (roff.size() - 1);
+        const uint8_t *src = query_residues + query_offsets[qi];
+        for (uint64_t j = 0; j < L; j++) reads.push_back(kComplement[src[L - 1 - j]]);
+        roff.push_back(reads.size());
+    }
+
+    // tasks of every hit that can be covered (Alignment.cpp:370-373)
+    std::vector<b200_nucl_task> tasks;
+    std::vector<uint64_t> task_hit;
+    std::vector<uint64_t> coff(1, 0);
+    std::vector<int64_t> hit_task(n_hits, -1);
+    for (uint32_t qi = 0; qi < n_queries; qi++) {
+        const int L = (int) (query_offsets[qi + 1] - query_offsets[qi]);
+        for (uint64_t k = hit_offsets[qi]; k < hit_offsets[qi + 1]; k++) {
+            const uint32_t t = hit_targets[k];
+            if (!can_be_covered(params->cov_thr, params->cov_mode, static_cast<float>(L), static_cast<float>(db_len[t]))) continue;
+            const bool rev = hit_reverse != nullptr && hit_reverse[k] != 0;
+            b200_nucl_task tk;
+            tk.query = rev ? rc_index[qi] : qi; tk.target = t; tk.diagonal = (uint16_t) hit_diagonals[k]; tk.reserved = 0;
+            hit_task[k] = (int64_t) tasks.size();
+            tasks.push_back(tk); task_hit.push_back(k);
+            coff.push_back(coff.back() + 2 * (uint64_t) L + 72);
+        }
+    }
+    std::vector<b200_nucl_aln> aln(tasks.size());
+    std::vector<uint32_t> cig(coff.back() + 1);
+    if (!tasks.empty()) {
+        int rc = b200_nucl_align(ctx, reads.data(), roff.data(), (uint32_t) (roff.size() - 1), tasks.data(), tasks.size(), params->gap_open,
+                                 params->gap_extend, zdrop, aln.data(), cig.data(), coff.data());
+        if (rc != B200_OK) return rc;
+    }
+
+    // result assembly (BandedNucleotideAligner.cpp:214-260 + Matcher.cpp:84-141 with alignmentMode SCORE_COV_SEQID), criteria, order
+    uint64_t n_aln = 0, bt_used = 0;
+    std::vector<b200_result> acc;
+    std::vector<std::string> acc_bt;
+    std::string bt;
+    for (uint32_t qi = 0; qi < n_queries; qi++) {
+        const int L = (int) (query_offsets[qi + 1] - query_offsets[qi]);
+        acc.clear(); acc_bt.clear();
+        uint32_t passed = 0, rejected = 0;
+        for (uint64_t k = hit_offsets[qi]; k < hit_offsets[qi + 1] && passed < params->max_accept && rejected < params->max_rejected; k++) {
+            if (hit_task[k] < 0) { rejected++; continue; }
+            n_aln++;
+            const b200_nucl_aln &a = aln[(size_t) hit_task[k]];
+            const uint32_t t = hit_targets[k];
+            const int tl = db_len[t];
+            const bool rev = hit_reverse != nullptr && hit_reverse[k] != 0;
+            bt.clear();
+            for (int c = 0; c < a.n_cigar; c++) {
+                const uint32_t op = cig[coff[(size_t) hit_task[k]] + c];
+                bt.append((size_t) (op >> 4), "MID"[op & 0xfu]);
+            }
+            const uint32_t score1 = (uint32_t) a.score;
+            const float qcov = compute_cov((unsigned) a.qstart, (unsigned) a.qend, (unsigned) L);
+            const float tcov = compute_cov((unsigned) a.dbstart, (unsigned) a.dbend, (unsigned) tl);
+            unsigned int aln_len = (unsigned int) (std::max(abs(a.qend - a.qstart), abs(a.dbend - a.dbstart)) + 1);
+            if (bt.size() > 0) aln_len = (unsigned int) bt.size();
+            b200_result r;
+            memset(&r, 0, sizeof(r));
+            r.db_key = target_keys ? target_keys[t] : t;
+            r.score = static_cast<int>(b200h_bit_score(evalue, (double) score1) + 0.5);
+            r.qcov = qcov; r.dbcov = tcov;
+            r.seq_id = compute_seq_id(params->seq_id_mode, a.identical, L, tl, (int) aln_len);
+            r.eval = b200h_evalue(evalue, (double) score1, (double) L);
+            r.aln_length = aln_len;
+            r.q_start = a.qstart; r.q_end = a.qend; r.q_len = L;
+            r.db_start = rev ? a.dbend : a.dbstart; r.db_end = rev ? a.dbstart : a.dbend; r.db_len = tl;
+            const uint32_t tkey = r.db_key;
+            const bool identity = params->include_identity && query_keys != nullptr && query_keys[qi] == tkey;
+            if (identity) { r.qcov = 1.0f; r.dbcov = 1.0f; r.seq_id = 1.0f; }
+            const bool ok = identity || ((r.eval <= params->eval_thr) && (r.seq_id >= (double) params->seq_id_thr) &&
+                                         has_coverage(params->cov_thr, params->cov_mode, r.qcov, r.dbcov) &&
+                                         ((int) r.aln_length >= params->aln_len_thr));
+            if (ok) {
+                r.bt_len = (uint32_t) bt.size();
+                r.bt_off = acc_bt.size();
+                acc.push_back(r); acc_bt.push_back(bt);
+                passed++; rejected = 0;
+            } else {
+                rejected++;
+            }
+        }
+        if (acc.size() > 1)
+            std::sort(acc.begin(), acc.end(), [](const b200_result &x, const b200_result &y) {
+                if (x.eval != y.eval) return x.eval < y.eval;
+                if (x.score != y.score) return x.score > y.score;
+                if (x.db_len != y.db_len) return x.db_len < y.db_len;
+                return x.db_key < y.db_key;
+            });
+        for (size_t i = 0; i < acc.size(); i++) {
+            const std::string &b = acc_bt[(size_t) acc[i].bt_off];
+            if (bt_used + b.size() > bt_cap || (b.size() > 0 && bt_pool == nullptr))
+                return b200_set_err(ctx, B200_ERR_RANGE, "b200_align_batch_nucl: backtrace pool too small");
+            if (!b.empty()) memcpy(bt_pool + bt_used, b.data(), b.size());
+            acc[i].bt_off = bt_used;
+            bt_used += b.size();
+            results[hit_offsets[qi] + i] = acc[i];
+        }
+        n_results[qi] = (uint32_t) acc.size();
+    }
+    if (n_alignments != nullptr) *n_alignments = n_aln;
+    return B200_OK;
+}
+

@@ -203,6 +203,29 @@ class Ref:
             raise RuntimeError("ref_align_query: buffer too small")
         return out.raw[:n], int(na.value), int(nacc.value)
 
+    def align_query_nucl(self, q, qkey, tdata, toff, hit_idx, hit_keys, hit_diag, hit_rev, db_residues, go=5, ge=2, zdrop=40,
+                         eval_thr=1e-3, cov_thr=0.0, cov_mode=0, seq_id_thr=0.0, aln_len_thr=0, seq_id_mode=0, max_accept=0x7fffffff,
+                         max_reject=0x7fffffff, include_identity=False, add_backtrace=True, compress=True):
+        """nucleotide `align` entry of one read -> (records text, n getSWResult calls, n accepted)"""
+        q = np.ascontiguousarray(q, np.uint8)
+        hi = np.ascontiguousarray(hit_idx, np.uint32); hk = np.ascontiguousarray(hit_keys, np.uint32)
+        hd = np.ascontiguousarray(hit_diag, np.int16)
+        hr = None if hit_rev is None else np.ascontiguousarray(hit_rev, np.uint8)
+        to = np.ascontiguousarray(toff, np.int64)
+        cap = 4096 + len(hi) * 4096
+        out = ctypes.create_string_buffer(cap)
+        na = ctypes.c_int64(0); nacc = ctypes.c_int64(0)
+        self.lib.ref_align_query_nucl.restype = ctypes.c_int64
+        n = self.lib.ref_align_query_nucl(_p(q), len(q), ctypes.c_uint32(qkey), _p(tdata), _p(to), _p(hi), _p(hk), _p(hd), _p(hr),
+                                          ctypes.c_int64(len(hi)), ctypes.c_int64(db_residues), go, ge, zdrop, ctypes.c_double(eval_thr),
+                                          ctypes.c_float(cov_thr), cov_mode, ctypes.c_float(seq_id_thr), aln_len_thr, seq_id_mode,
+                                          ctypes.c_uint32(max_accept), ctypes.c_uint32(max_reject), 1 if include_identity else 0,
+                                          1 if add_backtrace else 0, 1 if compress else 0, out, ctypes.c_int64(cap), ctypes.byref(na),
+                                          ctypes.byref(nacc))
+        if n < 0:
+            raise RuntimeError("ref_align_query_nucl: buffer too small")
+        return out.raw[:n], int(na.value), int(nacc.value)
+
     def result_to_buffer(self, db_key, score, seq_id, evalue, qs, qe, ql, ds, de, dl, backtrace=b"", add_backtrace=False, compress=True):
         out = ctypes.create_string_buffer(1024 + 2 * len(backtrace))
         self.lib.ref_result_to_buffer.restype = ctypes.c_int64

@@ -568,4 +568,74 @@ void ref_profile_diag(const int8_t *pssm, const unsigned char *consensus, int qL
     delete q;
 }
 
+// Nucleotide variant of ref_align_query: Matcher over BandedNucleotideAligner (Matcher.cpp:13-26,72-78).  hitDiag/hitRev = the
+// prefilter record's diagonal and strand (isReverse = reversePrefilterResult && prefScore < 0, Alignment.cpp:360).  The byte the
+// reference reads one past each sequence when reversing it is pinned to X as in ref_banded_nucl_align.
+int64_t ref_align_query_nucl(const unsigned char *q, int qL, uint32_t qKey, const unsigned char *tdata, const int64_t *toff,
+                             const uint32_t *hitIdx, const uint32_t *hitKeys, const int16_t *hitDiag, const uint8_t *hitRev,
+                             int64_t nHits, int64_t dbResidues, int gapOpen, int gapExtend, int zdrop, double evalThr, float covThr,
+                             int covMode, float seqIdThr, int alnLenThr, int seqIdMode, uint32_t maxAccept, uint32_t maxReject,
+                             int includeIdentity, int addBacktrace, int compress, char *out, int64_t cap, int64_t *nAligned,
+                             int64_t *nAccepted) {
+    size_t maxLen = qL;
+    for (int64_t i = 0; i < nHits; i++) maxLen = std::max(maxLen, (size_t) (toff[hitIdx[i] + 1] - toff[hitIdx[i]]));
+    maxLen += 64;
+    EvalueComputation evaluer((size_t) dbResidues, g_nt, gapOpen, gapExtend);
+    Matcher matcher(Parameters::DBTYPE_NUCLEOTIDES, (int) maxLen, g_nt, &evaluer, false, 1.0f, gapOpen, gapExtend, 0.0f, zdrop);
+    Sequence qSeq(maxLen, Parameters::DBTYPE_NUCLEOTIDES, g_nt, 0, false, false);
+    Sequence dbSeq(maxLen, Parameters::DBTYPE_NUCLEOTIDES, g_nt, 0, false, false);
+    std::string qAscii(qL, 'X'), tAscii;
+    for (int i = 0; i < qL; i++) qAscii[i] = g_nt->num2aa[q[i]];
+    qSeq.mapSequence(0, qKey, qAscii.c_str(), qL);
+    qSeq.numSequence[qL] = (unsigned char) (g_nt->alphabetSize - 1);
+    matcher.initQuery(&qSeq);
+    std::vector<Matcher::result_t> swResults;
+    size_t passedNum = 0;
+    unsigned int rejected = 0;
+    int64_t aligned = 0;
+    for (int64_t i = 0; i < nHits && passedNum < maxAccept && rejected < maxReject; i++) {
+        const unsigned char *t = tdata + toff[hitIdx[i]];
+        const int tL = (int) (toff[hitIdx[i] + 1] - toff[hitIdx[i]]);
+        tAscii.assign(tL, 'X');
+        for (int k = 0; k < tL; k++) tAscii[k] = g_nt->num2aa[t[k]];
+        dbSeq.mapSequence(hitIdx[i], hitKeys[i], tAscii.c_str(), tL);
+        dbSeq.numSequence[tL] = (unsigned char) (g_nt->alphabetSize - 1);
+        if (Util::canBeCovered(covThr, covMode, static_cast<float>(qL), static_cast<float>(dbSeq.L)) == false) {
+            rejected++;
+            continue;
+        }
+        const bool isIdentity = (qKey == hitKeys[i] && includeIdentity) ? true : false;
+        const bool isReverse = hitRev != NULL && hitRev[i] != 0;
+        Matcher::result_t res = matcher.getSWResult(&dbSeq, static_cast<int>(hitDiag[i]), isReverse, covMode, covThr, evalThr,
+                                                    Matcher::SCORE_COV_SEQID, seqIdMode, isIdentity, false);
+        aligned++;
+        if (isIdentity) { res.qcov = 1.0f; res.dbcov = 1.0f; res.seqId = 1.0f; }
+        const bool evalOk = (res.eval <= evalThr);
+        const bool seqIdOK = (res.seqId >= (double) seqIdThr);
+        const bool covOK = Util::hasCoverage(covThr, covMode, res.qcov, res.dbcov);
+        const bool alnLenOK = Util::hasAlignmentLength(alnLenThr, res.alnLength);
+        if (isIdentity || (evalOk && seqIdOK && covOK && alnLenOK)) {
+            swResults.emplace_back(res);
+            passedNum++;
+            rejected = 0;
+        } else {
+            rejected++;
+        }
+    }
+    if (swResults.size() > 1) std::sort(swResults.begin(), swResults.end(), Matcher::compareHits);
+    int64_t used = 0;
+    std::vector<char> buf;
+    for (size_t i = 0; i < swResults.size(); i++) {
+        buf.resize(1024 + 2 * swResults[i].backtrace.size());
+        const size_t len = Matcher::resultToBuffer(buf.data(), swResults[i], addBacktrace != 0, compress != 0, false);
+        if (used + (int64_t) len + 1 > cap) return -1;
+        memcpy(out + used, buf.data(), len);
+        used += (int64_t) len;
+    }
+    out[used] = '\0';
+    if (nAligned) *nAligned = aligned;
+    if (nAccepted) *nAccepted = (int64_t) swResults.size();
+    return used;
+}
+
 }  // extern "C"

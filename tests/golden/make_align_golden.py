@@ -20,7 +20,7 @@ from oracle.pyoracle import Ref  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-from align_configs import CONFIGS  # noqa: E402  (shared with tests/test_alignment_batch.py)
+from align_configs import CONFIGS, NUCL_CONFIGS  # noqa: E402  (shared with tests/test_alignment_batch.py)
 
 
 def hit_lists(ex, n_per_query=120):
@@ -103,6 +103,40 @@ def main():
                                         include_identity=True, add_backtrace=(mode == 2))
             texts.append(txt)
         out["self_mode%d_text" % mode] = np.array(texts)
+    # ---- nucleotide search: reads of nucl_v1.npz, their true hit first, decoys behind it, every third read on the reverse strand ----
+    nv = np.load(os.path.join(HERE, "nucl_v1.npz"))
+    ntd, nto = nv["tdata"], nv["toff"].astype(np.int64)
+    nqd, nqo, ntasks = nv["qdata"], nv["qoff"], nv["tasks"]
+    rng = np.random.default_rng(99)
+    comp = np.array([2, 3, 0, 1, 4], np.uint8)
+    n_t = len(nto) - 1
+    nkeys = (7 + 5 * np.arange(n_t)).astype(np.uint32)
+    reads, lists, diags, revs = [], [], [], []
+    for i in range(0, 600, 4):
+        qi, ti, dg = int(ntasks[i, 0]), int(ntasks[i, 1]), int(np.int16(np.uint16(ntasks[i, 2])))
+        r = nqd[int(nqo[qi]):int(nqo[qi + 1])].copy()
+        rev = (i // 4) % 3 == 2
+        if rev:
+            r = comp[r[::-1]]                      # the stored read is the reverse complement; the hit says "reverse strand"
+        decoys = rng.integers(0, n_t, 3)
+        reads.append(r)
+        lists.append(np.array([ti] + list(decoys), np.uint32))
+        diags.append(np.array([dg] + list(rng.integers(-100, 1500, 3)), np.int16))
+        revs.append(np.array([1 if rev else 0, 0, 1 if rev else 0, 0], np.uint8))
+    out["nucl_reads"] = np.concatenate(reads)
+    out["nucl_read_off"] = np.cumsum([0] + [len(r) for r in reads]).astype(np.uint64)
+    out["nucl_hit_targets"] = np.concatenate(lists)
+    out["nucl_hit_diags"] = np.concatenate(diags)
+    out["nucl_hit_rev"] = np.concatenate(revs)
+    out["nucl_target_keys"] = nkeys
+    for name, kw in NUCL_CONFIGS.items():
+        texts, nal = [], []
+        for k in range(len(reads)):
+            txt, na, _ = ref.align_query_nucl(reads[k], 900 + k, ntd, nto, lists[k], nkeys[lists[k]], diags[k], revs[k], int(nto[-1]), **kw)
+            texts.append(txt); nal.append(na)
+        out["cfg_%s_text" % name] = np.array(texts)
+        out["cfg_%s_naligned" % name] = np.array(nal, np.int64)
+        print(name, "records:", sum(t.count(b"\n") for t in texts), "alignments:", sum(nal))
     np.savez_compressed(os.path.join(HERE, "align_v1.npz"), **out)
     print("wrote align_v1.npz", os.path.getsize(os.path.join(HERE, "align_v1.npz")))
 

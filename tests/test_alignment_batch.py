@@ -29,6 +29,14 @@ def _params(name):
     return m.CONFIGS[name]
 
 
+def _nucl_params(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_align_golden_cfg", os.path.join(ROOT, "tests", "golden", "align_configs.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m.NUCL_CONFIGS[name]
+
+
 def _align_params(kw):
     kw = dict(kw)
     kw.pop("add_backtrace", None); kw.pop("compress", None)
@@ -138,6 +146,33 @@ def test_identity_hits(gold, ctx, submat, mode):
     texts = gold["self_mode%d_text" % mode]
     for qi in range(12):
         assert al.records(res[qi], pool, mode == 2, True) == bytes(texts[qi]), (mode, qi)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["nucl_default", "nucl_strict", "nucl_loose"])
+def test_nucleotide_alignment_entries_equal_reference(gold, ctx, name):
+    """the BandedNucleotideAligner branch of getSWResult through b200_align_batch_nucl: forward and reverse-strand hits"""
+    kw = _nucl_params(name)
+    nv = np.load(os.path.join(ROOT, "tests", "golden", "nucl_v1.npz"))
+    ctx.load_db(nv["tdata"], nv["toff"].astype(np.uint64), 5)
+    ro = gold["nucl_read_off"]
+    reads = [gold["nucl_reads"][int(ro[i]):int(ro[i + 1])] for i in range(len(ro) - 1)]
+    per = 4
+    lists = [gold["nucl_hit_targets"][per * i:per * (i + 1)] for i in range(len(reads))]
+    diags = [gold["nucl_hit_diags"][per * i:per * (i + 1)] for i in range(len(reads))]
+    revs = [gold["nucl_hit_rev"][per * i:per * (i + 1)] for i in range(len(reads))]
+    ev = al.EvalueParams.defaults("nucleotide.out", 5, 2, int(nv["toff"][-1]))
+    par = _align_params(dict(kw, gap_open=5, gap_extend=2))
+    res, pool, n_aln = al.align_batch_nucl(ctx, reads, lists, diags, revs, par, ev, zdrop=40, query_keys=900 + np.arange(len(reads)),
+                                           target_keys=gold["nucl_target_keys"])
+    texts = gold["cfg_%s_text" % name]
+    for k in range(len(reads)):
+        got = al.records(res[k], pool, kw.get("add_backtrace", True), kw.get("compress", True))
+        assert got == bytes(texts[k]), (name, k, got, bytes(texts[k]))
+    assert n_aln == int(gold["cfg_%s_naligned" % name].sum())
+    assert sum(len(r) for r in res) > 20
+    if name == "nucl_default":
+        assert sum(1 for k in range(len(reads)) if revs[k][0] and len(res[k])) >= 40      # reverse-strand hits are found
 
 
 @pytest.mark.gpu
