@@ -122,13 +122,13 @@ def align_batch(ctx, submat, queries, hit_lists, params, evalue, query_keys=None
             if len(hit_lists[qi]):
                 ids = np.minimum(np.asarray(hit_lists[qi], np.int64), len(lens) - 1)   # range errors are the library's to report
                 bt_cap += int(len(queries[qi]) * len(hit_lists[qi]) + lens[ids].sum())
-    pool = ctypes.create_string_buffer(bt_cap)
+    pool = np.empty(bt_cap, np.uint8)            # written by the library up to the last accepted backtrace; never read beyond
     rc = lib.b200_align_batch(ctx.h, _p(mat), _p(pb), int(submat.A), _p(qres), _p(qoff), _p(qk), ctypes.c_uint32(nq), _p(hoff), _p(htg),
-                              _p(tk), ctypes.byref(params), ctypes.byref(evalue), _p(res), _p(nres), pool, _u64(bt_cap),
+                              _p(tk), ctypes.byref(params), ctypes.byref(evalue), _p(res), _p(nres), _p(pool), _u64(bt_cap),
                               ctypes.byref(n_aln))
     ctx._check(rc)
-    out = [res[int(hoff[i]):int(hoff[i]) + int(nres[i])].copy() for i in range(nq)]
-    return out, pool.raw, int(n_aln.value)
+    out = [res[int(hoff[i]):int(hoff[i]) + int(nres[i])] for i in range(nq)]
+    return out, pool, int(n_aln.value)
 
 
 def align_batch_nucl(ctx, reads, hit_lists, hit_diagonals, hit_reverse, params, evalue, zdrop=40, query_keys=None, target_keys=None):
@@ -152,19 +152,19 @@ def align_batch_nucl(ctx, reads, hit_lists, hit_diagonals, hit_reverse, params, 
     nres = np.zeros(max(1, nq), np.uint32)
     n_aln = ctypes.c_uint64(0)
     bt_cap = 16 + sum((2 * len(reads[i]) + 72) * len(hit_lists[i]) for i in range(nq))
-    pool = ctypes.create_string_buffer(bt_cap)
+    pool = np.empty(bt_cap, np.uint8)
     rc = lib.b200_align_batch_nucl(ctx.h, _p(qres), _p(qoff), _p(qk), ctypes.c_uint32(nq), _p(hoff), _p(htg), _p(hdg), _p(hrv), _p(tk),
-                                   ctypes.byref(params), int(zdrop), ctypes.byref(evalue), _p(res), _p(nres), pool, _u64(bt_cap),
+                                   ctypes.byref(params), int(zdrop), ctypes.byref(evalue), _p(res), _p(nres), _p(pool), _u64(bt_cap),
                                    ctypes.byref(n_aln))
     ctx._check(rc)
-    out = [res[int(hoff[i]):int(hoff[i]) + int(nres[i])].copy() for i in range(nq)]
-    return out, pool.raw, int(n_aln.value)
+    out = [res[int(hoff[i]):int(hoff[i]) + int(nres[i])] for i in range(nq)]
+    return out, pool, int(n_aln.value)
 
 
 def records(results, pool, add_backtrace=True, compress=True):
     """The alignment DB entry of one query (what Alignment::run writes for it, Alignment.cpp:505-512)."""
     parts = []
     for r in results:
-        bt = pool[int(r["bt_off"]):int(r["bt_off"]) + int(r["bt_len"])]
+        bt = bytes(pool[int(r["bt_off"]):int(r["bt_off"]) + int(r["bt_len"])])
         parts.append(result_to_buffer(r, bt, add_backtrace, compress))
     return b"".join(parts)

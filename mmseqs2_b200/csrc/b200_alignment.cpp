@@ -4,12 +4,15 @@
 #include "b200_alignment.h"
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "b200_host.h"
@@ -268,6 +271,16 @@ float compute_seq_id(int mode, int ids, int ql, int tl, int aln_len) {
     return 0.0;
 }
 
+// body(first, last) over [0, n) on up to 16 host threads (the reference runs this part of Alignment::run under OpenMP too)
+template <typename F> void parallel_ranges(size_t n, size_t min_per_thread, F body) {
+    size_t nt = std::min<size_t>(std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency())), n / std::max<size_t>(1, min_per_thread));
+    if (nt <= 1) { body((size_t) 0, n); return; }
+    std::vector<std::thread> th;
+    const size_t step = (n + nt - 1) / nt;
+    for (size_t a = 0; a < n; a += step) th.emplace_back(body, a, std::min(n, a + step));
+    for (std::thread &t : th) t.join();
+}
+
 struct HitState {        // s_align of one (query, hit) as ssw_align leaves it
     uint32_t score1 = 0;
     int32_t q_start = -1, q_end = 0, db_start = -1, db_end = -1;
@@ -303,42 +316,56 @@ int b200_align_batch(b200_ctx *ctx, const int16_t *sub_matrix, const double *p_b
     const int A = alphabet;
     const int go = params->gap_open, ge = params->gap_extend;
     const int mode = params->sw_mode;
+    static const bool trace = getenv("B200_TRACE") != nullptr;   // stderr phase times (development aid)
+    typedef std::chrono::steady_clock Clock;
+    const Clock::time_point t0 = Clock::now();
+    Clock::time_point t_prof = t0, t_end = t0, t_start = t0, t_bt = t0;
+    float bt_kernel_ms = 0;
     const int32_t *db_len = ctx->h_len.data();   // read-only after b200_db_load
 
     // ---- Matcher::initQuery -> ssw_init for every query (host float/int8 logic, b200_host.h) -------------------------
     std::vector<std::vector<int8_t>> profiles(n_queries);
     std::vector<b200_query> queries(n_queries);
-    std::vector<float> fbias;
-    std::vector<int8_t> cb;
     for (uint32_t qi = 0; qi < n_queries; qi++) {
         if (query_offsets[qi + 1] < query_offsets[qi] || query_offsets[qi + 1] - query_offsets[qi] > 65535)
             return b200_set_err(ctx, B200_ERR_RANGE, "b200_align_batch: query length outside [0, 65535]");
-        const int L = (int) (query_offsets[qi + 1] - query_offsets[qi]);
-        const uint8_t *seq = query_residues + query_offsets[qi];
-        queries[qi].profile = nullptr; queries[qi].qlen = L; queries[qi].bias = 0;
-        if (L == 0) {
-            if (hit_offsets[qi + 1] != hit_offsets[qi]) return b200_set_err(ctx, B200_ERR_ARG, "b200_align_batch: empty query with hits");
-            continue;
+        if (query_offsets[qi + 1] == query_offsets[qi] && hit_offsets[qi + 1] != hit_offsets[qi])
+            return b200_set_err(ctx, B200_ERR_ARG, "b200_align_batch: empty query with hits");
+    }
+    std::vector<int> prof_rc(n_queries, 0);
+    parallel_ranges(n_queries, 16, [&](size_t qa, size_t qb) {
+        std::vector<float> fbias;
+        std::vector<int8_t> cb;
+        for (size_t qi = qa; qi < qb; qi++) {
+            const int L = (int) (query_offsets[qi + 1] - query_offsets[qi]);
+            const uint8_t *seq = query_residues + query_offsets[qi];
+            queries[qi].profile = nullptr; queries[qi].qlen = L; queries[qi].bias = 0;
+            if (L == 0) continue;
+            for (int j = 0; j < L; j++)
+                if (seq[j] >= A) prof_rc[qi] = B200_ERR_ARG;
+            if (prof_rc[qi] != 0) continue;
+            cb.assign((size_t) L, 0);
+            if (params->comp_bias) {
+                fbias.resize((size_t) L);
+                b200h_comp_bias(sub_matrix, p_back, A, seq, L, params->comp_bias_scale, fbias.data());
+                b200h_round_bias_ssw(fbias.data(), L, cb.data());
+            }
+            profiles[qi].resize((size_t) A * L);
+            if (b200h_build_profile(sub_matrix, A, seq, L, cb.data(), 1, profiles[qi].data()) != 0) { prof_rc[qi] = B200_ERR_RANGE; continue; }
+            queries[qi].profile = profiles[qi].data();
+            queries[qi].bias = b200h_ssw_bias(sub_matrix, A, cb.data(), L, params->comp_bias ? 1 : 0);
         }
-        for (int j = 0; j < L; j++)
-            if (seq[j] >= A) return b200_set_err(ctx, B200_ERR_ARG, "b200_align_batch: query residue code >= alphabet");
-        cb.assign((size_t) L, 0);
-        if (params->comp_bias) {
-            fbias.resize((size_t) L);
-            b200h_comp_bias(sub_matrix, p_back, A, seq, L, params->comp_bias_scale, fbias.data());
-            b200h_round_bias_ssw(fbias.data(), L, cb.data());
-        }
-        profiles[qi].resize((size_t) A * L);
-        if (b200h_build_profile(sub_matrix, A, seq, L, cb.data(), 1, profiles[qi].data()) != 0)
-            return b200_set_err(ctx, B200_ERR_RANGE, "b200_align_batch: profile value outside int8");
-        queries[qi].profile = profiles[qi].data();
-        queries[qi].bias = b200h_ssw_bias(sub_matrix, A, cb.data(), L, params->comp_bias ? 1 : 0);
+    });
+    for (uint32_t qi = 0; qi < n_queries; qi++) {
+        if (prof_rc[qi] == B200_ERR_ARG) return b200_set_err(ctx, B200_ERR_ARG, "b200_align_batch: query residue code >= alphabet");
+        if (prof_rc[qi] == B200_ERR_RANGE) return b200_set_err(ctx, B200_ERR_RANGE, "b200_align_batch: profile value outside int8");
     }
     // a query without hits never reaches initQuery; give the ABI a harmless one-residue stand-in
     static const int8_t kStub[64] = {0};
     for (uint32_t qi = 0; qi < n_queries; qi++)
         if (queries[qi].profile == nullptr) { queries[qi].profile = kStub; queries[qi].qlen = 1; queries[qi].bias = 0; }
 
+    t_prof = Clock::now();
     // ---- the pairs the reference would align (Alignment.cpp:346-381) -------------------------------------------------
     std::vector<HitState> st(n_hits);
     std::vector<b200_pair> pairs;
@@ -364,6 +391,7 @@ int b200_align_batch(b200_ctx *ctx, const int16_t *sub_matrix, const double *p_b
         int rc = b200_sw_score_endpos(ctx, queries.data(), (int) n_queries, pairs.data(), np, go, ge, ends.data());
         if (rc != B200_OK) return rc;
     }
+    t_end = Clock::now();
     // ---- ssw_align_private's gate (StripedSmithWaterman.cpp:846-863): host double / float math ------------------------
     std::vector<b200_pair> sub;
     std::vector<b200_sw_end> sub_ends;
@@ -387,6 +415,7 @@ int b200_align_batch(b200_ctx *ctx, const int16_t *sub_matrix, const double *p_b
         std::vector<b200_sw_aln> aln(sub.size());
         int rc = b200_sw_startpos(ctx, queries.data(), (int) n_queries, sub.data(), sub.size(), go, ge, sub_ends.data(), aln.data());
         if (rc != B200_OK) return rc;
+        t_start = Clock::now();
         std::vector<b200_pair> bt_pairs;
         std::vector<b200_sw_aln> bt_aln;
         std::vector<uint64_t> bt_hit;
@@ -406,23 +435,30 @@ int b200_align_batch(b200_ctx *ctx, const int16_t *sub_matrix, const double *p_b
             std::vector<const uint8_t *> qseq(n_queries);
             for (uint32_t qi = 0; qi < n_queries; qi++) qseq[qi] = query_residues + query_offsets[qi];
             std::vector<b200_sw_bt> bt(bt_pairs.size());
-            std::vector<uint32_t> cig(coff.back() + 1);
-            rc = b200_sw_backtrace(ctx, queries.data(), qseq.data(), (int) n_queries, bt_pairs.data(), bt_pairs.size(), go, ge,
-                                   bt_aln.data(), bt.data(), cig.data(), coff.data());
+            std::vector<uint32_t> cig_pool;
+            std::vector<uint64_t> cig_base;
+            rc = b200_sw_backtrace_impl(ctx, queries.data(), qseq.data(), (int) n_queries, bt_pairs.data(), bt_pairs.size(), go, ge,
+                                        bt_aln.data(), bt.data(), nullptr, nullptr, &cig_pool, &cig_base);
             if (rc != B200_OK) return rc;
-            for (size_t i = 0; i < bt_pairs.size(); i++) {
-                HitState &h = st[bt_hit[i]];
+            bt_kernel_ms = b200_last_kernel_ms(ctx);
+            for (size_t i = 0; i < bt_pairs.size(); i++)
                 if (!bt[i].ok) return b200_set_err(ctx, B200_ERR_CUDA, "b200_align_batch: backtrace did not reach the alignment score");
-                h.identical = (uint32_t) bt[i].identical;
-                h.backtrace.reserve((size_t) bt[i].bt_len);
-                for (int c = 0; c < bt[i].n_cigar; c++) {
-                    const uint32_t op = cig[coff[i] + c];
-                    h.backtrace.append((size_t) (op >> 4), "MID"[op & 0xfu]);
+            const uint32_t *cigp = cig_pool.data();
+            parallel_ranges(bt_pairs.size(), 512, [&](size_t a, size_t b) {
+                for (size_t i = a; i < b; i++) {
+                    HitState &h = st[bt_hit[i]];
+                    h.identical = (uint32_t) bt[i].identical;
+                    h.backtrace.reserve((size_t) bt[i].bt_len);
+                    for (int c = 0; c < bt[i].n_cigar; c++) {
+                        const uint32_t op = cigp[cig_base[i] + c];
+                        h.backtrace.append((size_t) (op >> 4), "MID"[op & 0xfu]);
+                    }
                 }
-            }
+            });
         }
     }
 
+    t_bt = Clock::now();
     // ---- getSWResult's assembly, checkCriteria, accept / reject walk, ordering (Matcher.cpp:84-141, Alignment.cpp:381-403) ----
     uint64_t n_aln = 0, bt_used = 0;
     std::vector<b200_result> acc;
@@ -508,6 +544,12 @@ int b200_align_batch(b200_ctx *ctx, const int16_t *sub_matrix, const double *p_b
         n_results[qi] = (uint32_t) acc.size();
     }
     if (n_alignments != nullptr) *n_alignments = n_aln;
+    if (trace) {
+        auto ms = [](Clock::time_point a, Clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[b200 trace] align_batch: %llu hits, profiles %.1f ms, score+end %.1f ms, gate+start %.1f ms, backtrace %.1f ms "
+                        "(kernels %.1f ms), assembly %.1f ms\n", (unsigned long long) n_hits, ms(t0, t_prof), ms(t_prof, t_end),
+                ms(t_end, t_start), ms(t_start, t_bt), bt_kernel_ms, ms(t_bt, Clock::now()));
+    }
     return B200_OK;
 }
 

@@ -96,4 +96,9 @@ struct b200_ctx {
 
 static inline int b200_set_err(b200_ctx *ctx, int code, const char *msg) { ctx->err = msg; return code; }
 
+// b200_sw_backtrace with the ops left in one dense pool (b200_backtrace.cu); the public entry point scatters them into the caller's slots
+int b200_sw_backtrace_impl(b200_ctx *ctx, const b200_query *queries, const uint8_t *const *query_seqs, int nq, const b200_pair *pairs,
+                           uint64_t n, int gap_open, int gap_extend, const b200_sw_aln *alns, b200_sw_bt *out, uint32_t *cigars,
+                           const uint64_t *cigar_offsets, std::vector<uint32_t> *pool_out, std::vector<uint64_t> *base_out);
+
 #endif  // B200_INTERNAL_H
