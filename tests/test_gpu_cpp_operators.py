@@ -65,3 +65,35 @@ def test_operator_mirror_matches_oracle(tmp_path, built_lib, oracle, blosum):
     counts = rest[101:101 + nh]
     c_exp, _ = oracle.diag(q, oracle.round_bias_diag(oracle.comp_bias(q)), res, to, ids, dg)
     assert np.array_equal(counts, c_exp.astype(np.int32))
+
+
+ALIGN_SRC = os.path.join(ROOT, "tests", "cpp", "align_batch_smoke.cpp")
+
+
+def test_align_batch_host_compiles_without_exceptions():
+    subprocess.check_call(["g++", "-std=c++11", "-fno-exceptions", "-Wall", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"), ALIGN_SRC])
+
+
+@pytest.mark.gpu
+def test_align_batch_from_cpp_host_writes_the_reference_entries(tmp_path, built_lib, blosum):
+    """b200_align_batch + b200h_result_to_buffer called from a C++ host: the entries equal the reference's `align -a` output"""
+    exe = str(tmp_path / "align_batch_smoke")
+    libdir = os.path.dirname(built_lib)
+    subprocess.check_call(["g++", "-std=c++11", "-fno-exceptions", "-O1", "-I" + os.path.join(ROOT, "include"), ALIGN_SRC,
+                           "-L" + libdir, "-lb200align", "-Wl,-rpath," + libdir, "-o", exe])
+    mat, pb = blosum
+    ex = np.load(os.path.join(ROOT, "tests", "golden", "examples_v1.npz"))
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "align_v1.npz"))
+    nq, nt = len(ex["qoff"]) - 1, len(ex["toff"]) - 1
+    inp, outp = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(inp, "wb") as f:
+        np.array([21, nt, nq, len(gold["hit_targets"]), 2], np.int32).tofile(f)
+        mat.astype(np.int16).tofile(f); pb.astype(np.float64).tofile(f)
+        ex["toff"].astype(np.uint64).tofile(f); ex["tdata"].tofile(f)
+        ex["qoff"].astype(np.uint64).tofile(f); ex["qdata"].tofile(f)
+        gold["hit_off"].astype(np.uint64).tofile(f); gold["hit_targets"].astype(np.uint32).tofile(f)
+        gold["target_keys"].astype(np.uint32).tofile(f); (5000 + np.arange(nq)).astype(np.uint32).tofile(f)
+    subprocess.check_call([exe, inp, outp])
+    entries = open(outp, "rb").read().split(b"\0")[:nq]
+    for qi in range(nq):
+        assert entries[qi] == bytes(gold["cfg_default_a_text"][qi]), qi
