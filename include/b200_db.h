@@ -1,0 +1,62 @@
+/* include/b200_db.h -- the on-disk formats either side of the hot path, host side only:
+ *
+ *   DB triple     <name> (entries, each followed by one NUL byte), <name>.index (text lines "key \t offset \t length \n", length
+ *                 counts the NUL; kept sorted by key), <name>.dbtype (int32, Parameters::DBTYPE_*)
+ *                 -- DBReader / DBWriter, src/commons/DBReader.cpp, DBWriter.cpp:401-420,483-494,654-667
+ *   sequence DB   entry = residues as ASCII + '\n' (+ NUL): sequence length = index length - 2 (DBReader::getSeqLen)
+ *   letters       ASCII -> numeric residue codes as Sequence::mapSequence applies them through BaseMatrix::aa2num
+ *                 (SubstitutionMatrix::setupLetterMapping, SubstitutionMatrix.cpp:257-298; NucleotideMatrix.cpp:17-62)
+ *
+ * and b200_align_db: the `align` module over DB files -- query DB + target DB + prefilter result DB -> alignment result DB --
+ * built on b200_align_batch (include/b200_alignment.h).  Uncompressed, single-part or ".0 .1 ..." split data files; no lookup /
+ * source / header files (not needed by the path).  Plain C ABI, status codes, no exceptions.
+ */
+#ifndef B200_DB_H
+#define B200_DB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "b200_alignment.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Parameters::DBTYPE_* (src/commons/Parameters.h) */
+enum { B200_DBTYPE_AMINO_ACIDS = 0, B200_DBTYPE_NUCLEOTIDES = 1, B200_DBTYPE_HMM_PROFILE = 2, B200_DBTYPE_ALIGNMENT_RES = 5,
+       B200_DBTYPE_PREFILTER_RES = 7 };
+
+typedef struct b200h_db b200h_db;
+/* Opens <data_path>, <data_path>.index and (if present) <data_path>.dbtype.  Entries are addressed by id = rank of the key
+ * (DBReader's order).  Returns B200_OK or B200_ERR_ARG (missing / malformed files; b200h_db_last_error() has the text). */
+int b200h_db_open(const char *data_path, b200h_db **out);
+void b200h_db_close(b200h_db *db);
+uint64_t b200h_db_size(const b200h_db *db);
+int b200h_db_type(const b200h_db *db);                          /* -1 when there is no .dbtype file */
+uint32_t b200h_db_key(const b200h_db *db, uint64_t id);
+const char *b200h_db_data(const b200h_db *db, uint64_t id);    /* the entry, NUL-terminated */
+uint64_t b200h_db_entry_len(const b200h_db *db, uint64_t id);  /* index length: payload + NUL */
+int64_t b200h_db_id(const b200h_db *db, uint32_t key);         /* DBReader::getId; -1 if the key is absent */
+const char *b200h_db_last_error(void);
+
+typedef struct b200h_dbw b200h_dbw;
+int b200h_dbw_open(const char *data_path, int dbtype, b200h_dbw **out);
+int b200h_dbw_write(b200h_dbw *w, uint32_t key, const char *data, uint64_t len);   /* payload; the NUL is appended */
+int b200h_dbw_close(b200h_dbw *w);                              /* index sorted by key + dbtype file; frees w */
+
+/* BaseMatrix::aa2num after setupLetterMapping.  num2aa: the matrix alphabet in numeric order (A letters, 'X' last). */
+void b200h_aa2num_table(const char *num2aa, int A, int nucleotide, uint8_t table[256]);
+
+/* `mmseqs align` on DB files (amino-acid sequence DBs): loads target_db into the context, walks prefilter_db in buckets of
+ * bucket_queries queries, writes alignment_db.  add_backtrace / compress as --add-backtrace / -a in the reference.
+ * n_alignments / n_records may be NULL. */
+int b200_align_db(b200_ctx *ctx, const char *query_db, const char *target_db, const char *prefilter_db, const char *alignment_db,
+                  const int16_t *sub_matrix, const double *p_back, const char *num2aa, int alphabet, const b200_align_params *params,
+                  const b200_evalue_params *evalue /* NULL: blosum62 11/1 defaults with the target DB's residue count */,
+                  int add_backtrace, uint32_t bucket_queries, uint64_t *n_alignments, uint64_t *n_records);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,98 @@
+"""ctypes binding of include/b200_db.h: the DB triple (data / .index / .dbtype) as DBReader / DBWriter define it, the letter mapping
+of Sequence::mapSequence, and the `align` module over DB files (b200_align_db).  Host-side formats; the DPs run in libb200align.so."""
+import ctypes
+
+import numpy as np
+
+from .api import B200Error, _p, _u64, _vp, load_library
+
+DBTYPE_AMINO_ACIDS, DBTYPE_NUCLEOTIDES, DBTYPE_HMM_PROFILE, DBTYPE_ALIGNMENT_RES, DBTYPE_PREFILTER_RES = 0, 1, 2, 5, 7
+
+
+def _lib():
+    lib = load_library()
+    lib.b200h_db_last_error.restype = ctypes.c_char_p
+    lib.b200h_db_size.restype = ctypes.c_uint64
+    lib.b200h_db_key.restype = ctypes.c_uint32
+    lib.b200h_db_data.restype = ctypes.c_void_p
+    lib.b200h_db_entry_len.restype = ctypes.c_uint64
+    lib.b200h_db_id.restype = ctypes.c_int64
+    for n in ("b200h_db_size", "b200h_db_type", "b200h_db_close"):
+        getattr(lib, n).argtypes = [_vp]
+    lib.b200h_db_key.argtypes = [_vp, ctypes.c_uint64]
+    lib.b200h_db_data.argtypes = [_vp, ctypes.c_uint64]
+    lib.b200h_db_entry_len.argtypes = [_vp, ctypes.c_uint64]
+    lib.b200h_db_id.argtypes = [_vp, ctypes.c_uint32]
+    return lib
+
+
+class DB:
+    """DBReader: entries by id = rank of the key."""
+
+    def __init__(self, path):
+        self.lib = _lib()
+        self.h = _vp()
+        if self.lib.b200h_db_open(path.encode(), ctypes.byref(self.h)) != 0:
+            raise B200Error(self.lib.b200h_db_last_error().decode())
+
+    def __len__(self):
+        return int(self.lib.b200h_db_size(self.h))
+
+    @property
+    def dbtype(self):
+        return int(self.lib.b200h_db_type(self.h))
+
+    def key(self, i):
+        return int(self.lib.b200h_db_key(self.h, i))
+
+    def entry_len(self, i):
+        return int(self.lib.b200h_db_entry_len(self.h, i))
+
+    def data(self, i):
+        """payload of entry i without its NUL terminator"""
+        return ctypes.string_at(self.lib.b200h_db_data(self.h, i), self.entry_len(i) - 1)
+
+    def id_of(self, key):
+        return int(self.lib.b200h_db_id(self.h, key))
+
+    def close(self):
+        if self.h:
+            self.lib.b200h_db_close(self.h)
+            self.h = None
+
+
+def write_db(path, dbtype, keys, entries):
+    """DBWriter with one thread: entries (bytes) under keys, in the given order."""
+    lib = _lib()
+    w = _vp()
+    if lib.b200h_dbw_open(path.encode(), int(dbtype), ctypes.byref(w)) != 0:
+        raise B200Error(lib.b200h_db_last_error().decode())
+    for k, e in zip(keys, entries):
+        if lib.b200h_dbw_write(w, ctypes.c_uint32(int(k)), e, _u64(len(e))) != 0:
+            raise B200Error(lib.b200h_db_last_error().decode())
+    if lib.b200h_dbw_close(w) != 0:
+        raise B200Error(lib.b200h_db_last_error().decode())
+
+
+def aa2num_table(alphabet, nucleotide=False):
+    """BaseMatrix::aa2num after setupLetterMapping for a matrix alphabet given in numeric order (bytes / str)."""
+    lib = _lib()
+    a = alphabet.encode() if isinstance(alphabet, str) else bytes(alphabet)
+    t = np.zeros(256, np.uint8)
+    lib.b200h_aa2num_table(a, len(a), 1 if nucleotide else 0, _p(t))
+    return t
+
+
+def align_db(ctx, submat, alphabet, query_db, target_db, prefilter_db, alignment_db, params, evalue=None, add_backtrace=True,
+             bucket_queries=4096):
+    """`mmseqs align` over DB files -> (number of alignments computed, number of records written)"""
+    lib = _lib()
+    a = alphabet.encode() if isinstance(alphabet, str) else bytes(alphabet)
+    mat = np.ascontiguousarray(submat.mat, np.int16)
+    pb = np.ascontiguousarray(submat.pback, np.float64)
+    na, nr = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    rc = lib.b200_align_db(ctx.h, query_db.encode(), target_db.encode(), prefilter_db.encode(), alignment_db.encode(), _p(mat), _p(pb), a,
+                           int(submat.A), ctypes.byref(params), None if evalue is None else ctypes.byref(evalue),
+                           1 if add_backtrace else 0, ctypes.c_uint32(bucket_queries), ctypes.byref(na), ctypes.byref(nr))
+    ctx._check(rc)
+    return int(na.value), int(nr.value)

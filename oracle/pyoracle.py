@@ -226,6 +226,27 @@ class Ref:
             raise RuntimeError("ref_align_query_nucl: buffer too small")
         return out.raw[:n], int(na.value), int(nacc.value)
 
+    # ---- DB triple through the reference's DBWriter / DBReader (ref_glue.cpp) ----
+    def db_write(self, path, dbtype, keys, entries):
+        keys = np.ascontiguousarray(keys, np.uint32)
+        off = np.zeros(len(entries) + 1, np.int64)
+        off[1:] = np.cumsum([len(e) for e in entries])
+        blob = b"".join(entries) + b"\0"
+        self.lib.ref_db_write(path.encode(), int(dbtype), _p(keys), blob, _p(off), ctypes.c_int64(len(entries)))
+
+    def db_read(self, path, max_entries=1 << 16, cap=1 << 24):
+        keys = np.zeros(max_entries, np.uint32); lens = np.zeros(max_entries, np.int64)
+        data = ctypes.create_string_buffer(cap)
+        used = ctypes.c_int64(0); ty = ctypes.c_int(0)
+        self.lib.ref_db_read.restype = ctypes.c_int64
+        n = self.lib.ref_db_read(path.encode(), _p(keys), _p(lens), data, ctypes.c_int64(cap), ctypes.byref(used), ctypes.byref(ty),
+                                 ctypes.c_int64(max_entries))
+        out, u = [], 0
+        raw = ctypes.string_at(data, int(used.value))
+        for i in range(n):
+            out.append(raw[u:u + int(lens[i]) - 1]); u += int(lens[i]) - 1
+        return keys[:n].copy(), lens[:n].copy(), out, int(ty.value)
+
     def result_to_buffer(self, db_key, score, seq_id, evalue, qs, qe, ql, ds, de, dl, backtrace=b"", add_backtrace=False, compress=True):
         out = ctypes.create_string_buffer(1024 + 2 * len(backtrace))
         self.lib.ref_result_to_buffer.restype = ctypes.c_int64

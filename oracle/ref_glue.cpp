@@ -41,6 +41,8 @@
 #include "EvalueComputation.h"
 #include "BandedNucleotideAligner.h"
 #include "Matcher.h"
+#include "DBReader.h"
+#include "DBWriter.h"
 #include "QueryMatcher.h"
 #include "ProfileStates.h"
 #include "Util.h"
@@ -636,6 +638,38 @@ int64_t ref_align_query_nucl(const unsigned char *q, int qL, uint32_t qKey, cons
     if (nAligned) *nAligned = aligned;
     if (nAccepted) *nAccepted = (int64_t) swResults.size();
     return used;
+}
+
+// ---- DB triple: the reference's own DBWriter / DBReader on real files --------------------------------
+// entries i = data[off[i] .. off[i+1]) written under keys[i] in the given order (one writer thread), closed with merge
+void ref_db_write(const char *path, int dbtype, const uint32_t *keys, const char *data, const int64_t *off, int64_t n) {
+    const std::string idx = std::string(path) + ".index";
+    DBWriter w(path, idx.c_str(), 1, 0, dbtype);
+    w.open();
+    for (int64_t i = 0; i < n; i++) w.writeData(data + off[i], (size_t) (off[i + 1] - off[i]), keys[i], 0);
+    w.close(true);
+}
+
+// reads a DB through DBReader (sorted by key); returns the number of entries; keys/lens (index length) per entry, payloads
+// (without the NUL) concatenated into data (cap bytes), *used = bytes written; dbtype via *dbtype
+int64_t ref_db_read(const char *path, uint32_t *keys, int64_t *lens, char *data, int64_t cap, int64_t *used, int *dbtype, int64_t maxEntries) {
+    const std::string idx = std::string(path) + ".index";
+    DBReader<unsigned int> r(path, idx.c_str(), 1, DBReader<unsigned int>::USE_INDEX | DBReader<unsigned int>::USE_DATA);
+    r.open(DBReader<unsigned int>::NOSORT);
+    const int64_t n = (int64_t) r.getSize();
+    int64_t u = 0;
+    for (int64_t i = 0; i < n && i < maxEntries; i++) {
+        keys[i] = r.getDbKey((size_t) i);
+        lens[i] = (int64_t) r.getEntryLen((size_t) i);
+        const char *d = r.getData((size_t) i, 0);
+        const int64_t l = lens[i] - 1;
+        if (u + l <= cap) memcpy(data + u, d, (size_t) l);
+        u += l;
+    }
+    *used = u;
+    *dbtype = r.getDbtype();
+    r.close();
+    return n;
 }
 
 }  // extern "C"

@@ -137,6 +137,22 @@ def main():
         out["cfg_%s_text" % name] = np.array(texts)
         out["cfg_%s_naligned" % name] = np.array(nal, np.int64)
         print(name, "records:", sum(t.count(b"\n") for t in texts), "alignments:", sum(nal))
+    # ---- DB triple: files written by the reference's DBWriter, and the `align` module's output DB for the default_a lists ----
+    import tempfile
+    tmp = tempfile.mkdtemp()
+    out["aa2num_aa"], out["aa2num_nt"] = ref.aa2num()[:255], ref.aa2num(nucl=True)[:255]     # byte 255 is outside the reference's table
+    wkeys = np.array([7, 3, 4000000000, 12, 5, 0], np.uint32)
+    wents = [b"abc\n", b"", b"17\t250\t0\n8\t31\t-5\n", b"x" * 1000, b"\n", b"MKV\n"]
+    ref.db_write(os.path.join(tmp, "w"), 7, wkeys, wents)
+    out["dbw_keys"] = wkeys
+    out["dbw_entries"] = np.array(wents, dtype=object).astype("S1000")
+    out["dbw_entry_len"] = np.array([len(e) for e in wents])
+    for suf, name in (("", "data"), (".index", "index"), (".dbtype", "dbtype")):
+        out["dbw_file_" + name] = np.frombuffer(open(os.path.join(tmp, "w" + suf), "rb").read(), np.uint8)
+    qkeys = 5000 + np.arange(len(qo) - 1)
+    ref.db_write(os.path.join(tmp, "aln"), 5, qkeys, [bytes(t) for t in out["cfg_default_a_text"]])     # one thread: id order, as `align --threads 1`
+    for suf, name in (("", "data"), (".index", "index"), (".dbtype", "dbtype")):
+        out["alndb_file_" + name] = np.frombuffer(open(os.path.join(tmp, "aln" + suf), "rb").read(), np.uint8)
     np.savez_compressed(os.path.join(HERE, "align_v1.npz"), **out)
     print("wrote align_v1.npz", os.path.getsize(os.path.join(HERE, "align_v1.npz")))
 
