@@ -56,6 +56,14 @@ int b200_align_db(b200_ctx *ctx, const char *query_db, const char *target_db, co
                   const b200_evalue_params *evalue /* NULL: blosum62 11/1 defaults with the target DB's residue count */,
                   int add_backtrace, uint32_t bucket_queries, uint64_t *n_alignments, uint64_t *n_records);
 
+/* `mmseqs ungappedprefilter` on DB files (amino-acid sequence queries, PREF_MODE_UNGAPPED: runFilterOnCpu / runFilterOnGpu,
+ * src/prefiltering/ungappedprefilter.cpp:346-482, :41-343): every query against every target with the saturating ungapped scorer,
+ * hits with score > min_diag_score, ordered by (score desc, target key asc), truncated to max_res_list_len, written as prefilter
+ * records "key \t score \t 0".  Identity inclusion (same query/target DB) is not applied.  n_hits may be NULL. */
+int b200_prefilter_db(b200_ctx *ctx, const char *query_db, const char *target_db, const char *prefilter_db, const int16_t *sub_matrix,
+                      const double *p_back, const char *num2aa, int alphabet, int comp_bias, float comp_bias_scale, int min_diag_score,
+                      uint32_t max_res_list_len, uint32_t bucket_queries, uint64_t *n_hits);
+
 #ifdef __cplusplus
 }
 #endif

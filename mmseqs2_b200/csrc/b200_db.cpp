@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include "b200_host.h"
 #include "b200_internal.h"
 
 namespace {
@@ -292,6 +293,115 @@ int b200_align_db(b200_ctx *ctx, const char *query_db, const char *target_db, co
     if (tdb != nullptr) b200h_db_close(tdb);
     if (n_alignments != nullptr) *n_alignments = total_aln;
     if (n_records != nullptr) *n_records = total_rec;
+    return rc;
+}
+
+namespace {
+// numeric residues of every entry of a sequence DB (Sequence::mapSequence: length = index length - 2)
+void load_sequences(const b200h_db *db, const uint8_t a2n[256], std::vector<uint8_t> &res, std::vector<uint64_t> &off, std::vector<uint32_t> &keys) {
+    const uint64_t n = b200h_db_size(db);
+    off.assign(n + 1, 0);
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t l = b200h_db_entry_len(db, i);
+        off[i + 1] = off[i] + (l >= 2 ? l - 2 : 0);
+    }
+    res.resize(off[n] + 1);
+    keys.resize(n);
+    for (uint64_t i = 0; i < n; i++) {
+        const char *s = b200h_db_data(db, i);
+        uint8_t *d = res.data() + off[i];
+        for (uint64_t j = 0; j < off[i + 1] - off[i]; j++) d[j] = a2n[(unsigned char) s[j]];
+        keys[i] = b200h_db_key(db, i);
+    }
+}
+}  // namespace
+
+int b200_prefilter_db(b200_ctx *ctx, const char *query_db, const char *target_db, const char *prefilter_db, const int16_t *sub_matrix,
+                      const double *p_back, const char *num2aa, int alphabet, int comp_bias, float comp_bias_scale, int min_diag_score,
+                      uint32_t max_res_list_len, uint32_t bucket_queries, uint64_t *n_hits) {
+    if (ctx == nullptr) return B200_ERR_ARG;
+    if (query_db == nullptr || target_db == nullptr || prefilter_db == nullptr || sub_matrix == nullptr || p_back == nullptr ||
+        num2aa == nullptr || max_res_list_len == 0)
+        return b200_set_err(ctx, B200_ERR_ARG, "b200_prefilter_db: bad argument");
+    if (bucket_queries == 0) bucket_queries = 64;
+    b200h_db *tdb = nullptr, *qdb = nullptr;
+    b200h_dbw *out = nullptr;
+    int rc = b200h_db_open(target_db, &tdb);
+    if (rc == B200_OK) rc = b200h_db_open(query_db, &qdb);
+    if (rc == B200_OK) rc = b200h_dbw_open(prefilter_db, B200_DBTYPE_PREFILTER_RES, &out);
+    if (rc != B200_OK) b200_set_err(ctx, rc, g_db_err.c_str());
+    uint64_t total = 0;
+    if (rc == B200_OK) {
+        uint8_t a2n[256];
+        b200h_aa2num_table(num2aa, alphabet, 0, a2n);
+        std::vector<uint8_t> tres, qres;
+        std::vector<uint64_t> toff, qoff;
+        std::vector<uint32_t> tkeys, qkeys;
+        load_sequences(tdb, a2n, tres, toff, tkeys);
+        load_sequences(qdb, a2n, qres, qoff, qkeys);
+        rc = b200_db_load(ctx, tres.data(), toff.data(), tkeys.size(), alphabet);
+        const uint64_t nq = qkeys.size();
+        const int A = alphabet;
+        std::vector<std::vector<int8_t>> profiles;
+        std::vector<b200_query> queries;
+        std::vector<b200_hit> hits;
+        std::vector<uint32_t> nh;
+        std::vector<float> fbias;
+        std::vector<int8_t> cb;
+        std::vector<char> entry;
+        char line[64];
+        for (uint64_t b0 = 0; b0 < nq && rc == B200_OK; b0 += bucket_queries) {
+            const uint64_t b1 = std::min<uint64_t>(nq, b0 + bucket_queries);
+            const int nb = (int) (b1 - b0);
+            profiles.assign(nb, std::vector<int8_t>());
+            queries.assign(nb, b200_query());
+            std::vector<int> live;              // zero-length queries get an empty entry without touching the device
+            for (int i = 0; i < nb; i++) {
+                const uint64_t qi = b0 + i;
+                const int L = (int) (qoff[qi + 1] - qoff[qi]);
+                if (L == 0) continue;
+                const uint8_t *seq = qres.data() + qoff[qi];
+                // the profile ungappedprefilter.cpp:186-203 hands to the scorer: matrix column + rounded composition bias
+                cb.assign((size_t) L, 0);
+                if (comp_bias) {
+                    fbias.resize((size_t) L);
+                    b200h_comp_bias(sub_matrix, p_back, A, seq, L, comp_bias_scale, fbias.data());
+                    b200h_round_bias_ssw(fbias.data(), L, cb.data());
+                }
+                profiles[i].resize((size_t) A * L);
+                if (b200h_build_profile(sub_matrix, A, seq, L, cb.data(), 1, profiles[i].data()) != 0) { rc = b200_set_err(ctx, B200_ERR_RANGE, "b200_prefilter_db: profile value outside int8"); break; }
+                b200_query q; q.profile = profiles[i].data(); q.qlen = L; q.bias = b200h_ssw_bias(sub_matrix, A, cb.data(), L, comp_bias ? 1 : 0);
+                queries[live.size()] = q;
+                live.push_back(i);
+            }
+            if (rc != B200_OK) break;
+            hits.resize((size_t) live.size() * max_res_list_len + 1);
+            nh.assign(live.size() + 1, 0);
+            if (!live.empty())
+                rc = b200_ungapped_scan(ctx, queries.data(), (int) live.size(), min_diag_score, max_res_list_len, hits.data(), nh.data(), nullptr);
+            if (rc != B200_OK) break;
+            size_t lk = 0;
+            for (int i = 0; i < nb; i++) {
+                entry.clear();
+                if (lk < live.size() && live[lk] == i) {
+                    // device order is (score desc, DB-local id asc); ids are key ranks, so this is compareHitsByScoreAndId on keys
+                    for (uint32_t k = 0; k < nh[lk]; k++) {
+                        const b200_hit &h = hits[lk * max_res_list_len + k];
+                        b200_pref_hit ph; ph.seq_id = tkeys[h.id]; ph.pref_score = h.score; ph.diagonal = 0; ph.pad_ = 0;
+                        const size_t len = b200h_prefilter_hit_to_buffer(line, &ph);
+                        entry.insert(entry.end(), line, line + len);
+                    }
+                    total += nh[lk];
+                    lk++;
+                }
+                if (b200h_dbw_write(out, qkeys[b0 + i], entry.data(), entry.size()) != B200_OK) { rc = b200_set_err(ctx, B200_ERR_ARG, g_db_err.c_str()); break; }
+            }
+        }
+    }
+    if (out != nullptr && b200h_dbw_close(out) != B200_OK && rc == B200_OK) rc = b200_set_err(ctx, B200_ERR_ARG, g_db_err.c_str());
+    if (qdb != nullptr) b200h_db_close(qdb);
+    if (tdb != nullptr) b200h_db_close(tdb);
+    if (n_hits != nullptr) *n_hits = total;
     return rc;
 }
 

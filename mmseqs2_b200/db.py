@@ -96,3 +96,18 @@ def align_db(ctx, submat, alphabet, query_db, target_db, prefilter_db, alignment
                            1 if add_backtrace else 0, ctypes.c_uint32(bucket_queries), ctypes.byref(na), ctypes.byref(nr))
     ctx._check(rc)
     return int(na.value), int(nr.value)
+
+
+def prefilter_db(ctx, submat, alphabet, query_db, target_db, prefilter_db_path, comp_bias=True, comp_bias_scale=1.0, min_diag_score=15,
+                 max_res_list_len=300, bucket_queries=64):
+    """`mmseqs ungappedprefilter` over DB files -> number of hits written"""
+    lib = _lib()
+    a = alphabet.encode() if isinstance(alphabet, str) else bytes(alphabet)
+    mat = np.ascontiguousarray(submat.mat, np.int16)
+    pb = np.ascontiguousarray(submat.pback, np.float64)
+    nh = ctypes.c_uint64(0)
+    rc = lib.b200_prefilter_db(ctx.h, query_db.encode(), target_db.encode(), prefilter_db_path.encode(), _p(mat), _p(pb), a, int(submat.A),
+                               1 if comp_bias else 0, ctypes.c_float(comp_bias_scale), int(min_diag_score), ctypes.c_uint32(max_res_list_len),
+                               ctypes.c_uint32(bucket_queries), ctypes.byref(nh))
+    ctx._check(rc)
+    return int(nh.value)

@@ -153,6 +153,19 @@ def main():
     ref.db_write(os.path.join(tmp, "aln"), 5, qkeys, [bytes(t) for t in out["cfg_default_a_text"]])     # one thread: id order, as `align --threads 1`
     for suf, name in (("", "data"), (".index", "index"), (".dbtype", "dbtype")):
         out["alndb_file_" + name] = np.frombuffer(open(os.path.join(tmp, "aln" + suf), "rb").read(), np.uint8)
+    # ---- `ungappedprefilter` output DB for the example queries (runFilterOnCpu, ungappedprefilter.cpp:418-478): the reference's
+    #      ungapped_alignment scores, > 15, ordered by (score desc, key asc), at most 300 per query, written by its DBWriter
+    pref_entries = []
+    for qi in range(len(qo) - 1):
+        q = qd[int(qo[qi]):int(qo[qi + 1])]
+        sc = ref.ungapped(q, 1, td, to)
+        ids = np.nonzero(sc > 15)[0]
+        order = ids[np.lexsort((tkeys[ids], -sc[ids]))][:300]
+        pref_entries.append(b"".join(b"%d\t%d\t0\n" % (int(tkeys[t]), int(sc[t])) for t in order))
+    ref.db_write(os.path.join(tmp, "pref"), 7, qkeys, pref_entries)
+    for suf, name in (("", "data"), (".index", "index"), (".dbtype", "dbtype")):
+        out["prefdb_file_" + name] = np.frombuffer(open(os.path.join(tmp, "pref" + suf), "rb").read(), np.uint8)
+    print("prefilter DB:", sum(e.count(b"\n") for e in pref_entries), "hits")
     np.savez_compressed(os.path.join(HERE, "align_v1.npz"), **out)
     print("wrote align_v1.npz", os.path.getsize(os.path.join(HERE, "align_v1.npz")))
 

@@ -105,3 +105,30 @@ def test_align_module_over_db_files(gold, ctx, submat, tmp_path):
     for suf, name in (("", "data"), (".index", "index"), (".dbtype", "dbtype")):
         assert open(str(tmp_path / "aln") + suf, "rb").read() == gold["alndb_file_" + name].tobytes(), name
     assert n_aln == int(gold["cfg_default_a_naligned"].sum()) and n_rec == sum(bytes(t).count(b"\n") for t in gold["cfg_default_a_text"])
+
+
+@pytest.mark.gpu
+def test_prefilter_module_over_db_files_and_search(gold, ctx, submat, tmp_path):
+    """`ungappedprefilter` on DB files: the prefilter DB equals the one built from the reference's own scores; then `align` on that DB
+    runs end to end (search --prefilter-mode 1 without a reference process in the loop)"""
+    ex = np.load(os.path.join(ROOT, "tests", "golden", "examples_v1.npz"))
+    b = np.load(os.path.join(ROOT, "tests", "golden", "blosum62.npz"))
+    letters = b["alphabet"]
+    nq, nt = len(ex["qoff"]) - 1, len(ex["toff"]) - 1
+
+    def ascii_entries(data, off, n):
+        return [letters[data[int(off[i]):int(off[i + 1])]].tobytes() + b"\n" for i in range(n)]
+
+    db.write_db(str(tmp_path / "target"), db.DBTYPE_AMINO_ACIDS, gold["target_keys"], ascii_entries(ex["tdata"], ex["toff"], nt))
+    db.write_db(str(tmp_path / "query"), db.DBTYPE_AMINO_ACIDS, 5000 + np.arange(nq), ascii_entries(ex["qdata"], ex["qoff"], nq))
+    n_hits = db.prefilter_db(ctx, submat, bytes(letters), str(tmp_path / "query"), str(tmp_path / "target"), str(tmp_path / "pref"),
+                             bucket_queries=7)
+    for suf, name in (("", "data"), (".index", "index"), (".dbtype", "dbtype")):
+        assert open(str(tmp_path / "pref") + suf, "rb").read() == gold["prefdb_file_" + name].tobytes(), name
+    assert n_hits == gold["prefdb_file_data"].tobytes().count(b"\n")
+    n_aln, n_rec = db.align_db(ctx, submat, bytes(letters), str(tmp_path / "query"), str(tmp_path / "target"), str(tmp_path / "pref"),
+                               str(tmp_path / "aln"), al.AlignParams(sw_mode=al.SCORE_COV_SEQID, eval_thr=1e-3))
+    res = db.DB(str(tmp_path / "aln"))
+    assert len(res) == nq and res.dbtype == db.DBTYPE_ALIGNMENT_RES and n_aln == n_hits
+    assert sum(res.data(i).count(b"\n") for i in range(nq)) == n_rec > 100
+    res.close()
