@@ -102,6 +102,37 @@ def test_backtrace_matches_reference_outputs(ctx, golden, golden_db, submat):
     assert checked > 2000
 
 
+def test_backtrace_gap_penalties_and_wide_bands(ctx, oracle, submat, blosum):
+    """A6 against the oracle for gap costs other than 11/1 (go > ge, go == ge, go < ge: the warp kernel's F chain uses min(go, ge))
+    and for alignments whose band has to double many times (long indels; bands beyond the shared-memory rows)"""
+    rng = np.random.default_rng(4242)
+    bg = synth.background(blosum[1])
+    q = synth.random_seqs(rng, 1, bg, mean=600, sigma=0, lo=600, hi=600, normal=True)[0]
+    tg = [synth.mutate(rng, q, bg, s, i) for s, i in ((0.1, 0.02), (0.3, 0.05), (0.2, 0.0), (0.05, 0.1), (0.4, 0.03))]
+    tg.append(np.concatenate([q[:200], q[420:]]))                                    # one 220-residue deletion: band >= 220
+    tg.append(np.concatenate([q[:100], synth.random_seqs(rng, 1, bg, mean=300, sigma=0, lo=300, hi=300, normal=True)[0], q[100:]]))
+    tg.append(q[50:550].copy())
+    tg += [synth.mutate(rng, q[a:a + 250], bg, 0.25, 0.04) for a in (0, 100, 350)]
+    td, to = pack_targets(tg)
+    ctx.load_db(td, to.astype(np.uint64), 21)
+    prof = submat.ssw_query(q)
+    cb, bias = oracle.query_cb(q, True)
+    pairs = np.array([(0, t) for t in range(len(tg))], np.uint32)
+    checked = 0
+    for go, ge in ((11, 1), (5, 2), (3, 3), (2, 4), (20, 1)):
+        aln = ctx.sw_align([prof], pairs, go=go, ge=ge)
+        out, bts = ctx.sw_backtrace([prof], [q], pairs, aln, go=go, ge=ge)
+        for k in range(len(tg)):
+            if aln["dbend"][k] == -1:
+                continue
+            row = [int(aln[f][k]) for f in ("score", "qstart", "qend", "dbstart", "dbend")]
+            exp_bt, exp_id = oracle.backtrace(q, cb, tg[k], row, go, ge)
+            assert exp_bt is not None and out["ok"][k] == 1, (go, ge, k)
+            assert bts[k] == exp_bt and out["identical"][k] == exp_id, (go, ge, k)
+            checked += 1
+    assert checked >= 40
+
+
 def test_diag_matches_reference_outputs(ctx, golden, golden_db, submat):
     for qi, q in enumerate(_queries(golden)):
         ids, dg = golden["q%d_diag_ids" % qi], golden["q%d_diag_dg" % qi]
