@@ -104,6 +104,10 @@ int b200_sw_score(b200_ctx *ctx, const b200_query *queries, int n_queries, const
                   int gap_open, int gap_extend, int32_t *scores);
 int b200_sw_score_endpos(b200_ctx *ctx, const b200_query *queries, int n_queries, const b200_pair *pairs, uint64_t n,
                          int gap_open, int gap_extend, b200_sw_end *out);
+/* End positions for known scores (scores[i] = the pair's alignment score as b200_sw_score returns it; pairs with score 0 come back
+ * as "no residue aligned", dbend -1).  For hosts that gate on the score between the two steps, e.g. by E-value (b200_align_batch). */
+int b200_sw_endpos(b200_ctx *ctx, const b200_query *queries, int n_queries, const b200_pair *pairs, uint64_t n, int gap_open,
+                   int gap_extend, const int32_t *scores, b200_sw_end *out);
 /* ends[i] is the result of b200_sw_score_endpos for pairs[i]; pairs with ends[i].dbend == -1 are passed through */
 int b200_sw_startpos(b200_ctx *ctx, const b200_query *queries, int n_queries, const b200_pair *pairs, uint64_t n,
                      int gap_open, int gap_extend, const b200_sw_end *ends, b200_sw_aln *out);

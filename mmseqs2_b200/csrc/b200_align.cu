@@ -2111,6 +2111,60 @@ int b200_sw_score(b200_ctx *ctx, const b200_query *queries, int nq, const b200_p
     return B200_OK;
 }
 
+// End positions for pairs whose score is already known (a host that gates on the score between the two steps, as
+// b200_align_batch does with the E-value): packed FIND pass for the int16-safe pairs, int32 score+end kernel for the rest.
+int b200_sw_endpos(b200_ctx *ctx, const b200_query *queries, int nq, const b200_pair *pairs, uint64_t n, int go, int ge,
+                   const int32_t *scores, b200_sw_end *out) {
+    if (ctx == nullptr) return B200_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_pairs(ctx, queries, nq, pairs, n, go, ge);
+    if (rc != B200_OK) return rc;
+    if (n == 0) return B200_OK;
+    if (scores == nullptr || out == nullptr) return set_err(ctx, B200_ERR_ARG, "sw_endpos: NULL argument");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<QueryDesc> h_qd;
+    rc = stage_queries(ctx, queries, nq, true, h_qd);
+    if (rc != B200_OK) return rc;
+    const int A = ctx->alphabet;
+    std::vector<int> smax(nq, 1);
+    for (int i = 0; i < nq; i++) {
+        int m = 1;
+        const int8_t *pr = queries[i].profile;
+        for (size_t k = 0; k < (size_t) A * queries[i].qlen; k++) m = std::max(m, (int) pr[k]);
+        smax[i] = m;
+    }
+    std::vector<uint8_t> need(n, 0), rest(n, 0);
+    bool any_rest = false, any_need = false;
+    for (uint64_t i = 0; i < n; i++) {
+        const int qi = (int) pairs[i].query;
+        const bool ok = go >= ge && (int64_t) std::min(queries[qi].qlen, ctx->h_len[pairs[i].target]) * smax[qi] < 32000;
+        if (scores[i] < 0) return set_err(ctx, B200_ERR_ARG, "sw_endpos: negative score");
+        if (ok) { need[i] = scores[i] > 0 ? 1 : 0; any_need |= need[i] != 0; }
+        else { rest[i] = 1; any_rest = true; }
+    }
+    std::vector<int4> res4(n, make_int4(0, -1, -1, 0));
+    if (any_need) {
+        std::vector<int32_t> pos(2 * n, -1);
+        rc = run_sw16_pass(ctx, h_qd, queries, pairs, n, need.data(), scores, go, ge, pos);
+        if (rc != B200_OK) return rc;
+        for (uint64_t i = 0; i < n; i++) {
+            if (!need[i]) continue;
+            if (pos[2 * i] < 0 || pos[2 * i] > 0xfffe) return set_err(ctx, B200_ERR_ARG, "sw_endpos: a given score is not the pair's alignment score");
+            res4[i] = make_int4(scores[i], pos[2 * i], pos[2 * i + 1], 0);
+        }
+    }
+    if (any_rest) {
+        SwPlan plan;
+        plan_pairs(ctx, queries, pairs, n, rest.data(), plan);
+        std::vector<int4> res;
+        rc = run_sw_pass<1>(ctx, h_qd, pairs, plan, nullptr, go, ge, res);
+        if (rc != B200_OK) return rc;
+        for (uint32_t s2 = 0; s2 < plan.perm.size(); s2++) res4[plan.perm[s2]] = res[s2];
+    }
+    for (uint64_t i = 0; i < n; i++) report_end(res4[i], queries[pairs[i].query].bias, out[i]);
+    return B200_OK;
+}
+
 int b200_job_run(b200_job *job) {
     if (job == nullptr) return B200_ERR_ARG;
     b200_ctx *ctx = job->ctx;

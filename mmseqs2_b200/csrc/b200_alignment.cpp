@@ -384,31 +384,47 @@ int b200_align_batch(b200_ctx *ctx, const int16_t *sub_matrix, const double *p_b
         }
     }
 
-    // ---- alignScoreEndPos for all of them: packed score + end position launches ---------------------------------------
+    // ---- alignScoreEndPos, split at the E-value gate: the score of every pair (packed score launch), then end positions only
+    //      for the pairs whose E-value passes -- a hit that fails it is rejected by checkCriteria whatever its positions are
+    //      (Alignment.cpp:549-566), and in a search most prefilter hits fail it
     const uint64_t np = pairs.size();
-    std::vector<b200_sw_end> ends(np);
+    std::vector<int32_t> scores(np, 0);
     if (np > 0) {
-        int rc = b200_sw_score_endpos(ctx, queries.data(), (int) n_queries, pairs.data(), np, go, ge, ends.data());
+        int rc = b200_sw_score(ctx, queries.data(), (int) n_queries, pairs.data(), np, go, ge, scores.data());
         if (rc != B200_OK) return rc;
     }
-    t_end = Clock::now();
-    // ---- ssw_align_private's gate (StripedSmithWaterman.cpp:846-863): host double / float math ------------------------
-    std::vector<b200_pair> sub;
-    std::vector<b200_sw_end> sub_ends;
-    std::vector<uint64_t> sub_hit;
+    std::vector<b200_pair> epairs;
+    std::vector<int32_t> escores;
+    std::vector<uint64_t> ehit;
     for (uint64_t i = 0; i < np; i++) {
         HitState &h = st[pair_hit[i]];
         const int L = queries[pairs[i].query].qlen;
-        h.score1 = (uint32_t) ends[i].score; h.q_end = ends[i].qend; h.db_end = ends[i].dbend;
-        if (ends[i].dbend == -1) continue;     // "no residue could be aligned": the reference returns uninitialised fields
+        h.score1 = (uint32_t) scores[i]; h.q_end = L - 1; h.db_end = -1;
+        if (scores[i] <= 0) continue;          // "no residue could be aligned": the reference returns uninitialised fields
         h.defined = true;
-        h.qcov = compute_cov(0, (unsigned) h.q_end, (unsigned) L);
-        h.tcov = compute_cov(0, (unsigned) h.db_end, (unsigned) db_len[pairs[i].target]);
-        const bool low_cov = !has_coverage(params->cov_thr, params->cov_mode, h.qcov, h.tcov);
         h.evalue = b200h_evalue(evalue, (double) h.score1, (double) L);
-        const bool low_eval = h.evalue > params->eval_thr;
-        if (mode == 0 || low_eval || low_cov) continue;
-        sub.push_back(pairs[i]); sub_ends.push_back(ends[i]); sub_hit.push_back(pair_hit[i]);
+        if (h.evalue > params->eval_thr) continue;
+        epairs.push_back(pairs[i]); escores.push_back(scores[i]); ehit.push_back(pair_hit[i]);
+    }
+    std::vector<b200_sw_end> ends(epairs.size());
+    if (!epairs.empty()) {
+        int rc = b200_sw_endpos(ctx, queries.data(), (int) n_queries, epairs.data(), epairs.size(), go, ge, escores.data(), ends.data());
+        if (rc != B200_OK) return rc;
+    }
+    t_end = Clock::now();
+    // ---- the coverage half of ssw_align_private's gate (StripedSmithWaterman.cpp:846-863): host float math -----------------
+    std::vector<b200_pair> sub;
+    std::vector<b200_sw_end> sub_ends;
+    std::vector<uint64_t> sub_hit;
+    for (uint64_t i = 0; i < epairs.size(); i++) {
+        HitState &h = st[ehit[i]];
+        const int L = queries[epairs[i].query].qlen;
+        h.q_end = ends[i].qend; h.db_end = ends[i].dbend;
+        h.qcov = compute_cov(0, (unsigned) h.q_end, (unsigned) L);
+        h.tcov = compute_cov(0, (unsigned) h.db_end, (unsigned) db_len[epairs[i].target]);
+        const bool low_cov = !has_coverage(params->cov_thr, params->cov_mode, h.qcov, h.tcov);
+        if (mode == 0 || low_cov) continue;
+        sub.push_back(epairs[i]); sub_ends.push_back(ends[i]); sub_hit.push_back(ehit[i]);
     }
     // ---- alignStartPosBacktrace: reverse pass, then (mode 2) banded_sw + computerBacktrace for what still has coverage -----
     if (!sub.empty()) {
