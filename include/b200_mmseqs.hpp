@@ -248,16 +248,17 @@ public:
         int rc = b200_sw_score(dev_->ctx(), &q, 1, pairs.data(), n, gapOpen, gapExtend, score.data());
         if (rc != B200_OK) return rc;
         std::vector<b200_pair> sub;
+        std::vector<int32_t> subScore;
         std::vector<size_t> idx;
         for (size_t i = 0; i < n; i++) {
             s_align &r = out[i];
             r.score1 = (uint32_t) score[i]; r.dbStartPos1 = -1; r.qStartPos1 = -1; r.dbEndPos1 = -1; r.qEndPos1 = qlen_ - 1;
             r.qCov = 0; r.tCov = 0; r.word = (score[i] + bias_ >= 255) ? 1 : 0; r.identicalAACnt = 0; r.backtrace.clear();
-            if (score[i] > 0 && (gateScore == NULL || gateScore(r.score1, userData))) { sub.push_back(pairs[i]); idx.push_back(i); }
+            if (score[i] > 0 && (gateScore == NULL || gateScore(r.score1, userData))) { sub.push_back(pairs[i]); subScore.push_back(score[i]); idx.push_back(i); }
         }
         if (sub.empty()) { targets_.clear(); return B200_OK; }
         std::vector<b200_sw_end> ends(sub.size());
-        rc = b200_sw_score_endpos(dev_->ctx(), &q, 1, sub.data(), sub.size(), gapOpen, gapExtend, ends.data());
+        rc = b200_sw_endpos(dev_->ctx(), &q, 1, sub.data(), sub.size(), gapOpen, gapExtend, subScore.data(), ends.data());   // known scores
         if (rc != B200_OK) return rc;
         std::vector<b200_pair> sub2;
         std::vector<b200_sw_end> ends2;

@@ -247,6 +247,16 @@ class Ref:
             out.append(raw[u:u + int(lens[i]) - 1]); u += int(lens[i]) - 1
         return keys[:n].copy(), lens[:n].copy(), out, int(ty.value)
 
+    def gpuserver_query(self, shm_name, q, profile, cap=4096):
+        """one request through the reference's GPUSharedMemory client side (ref_glue.cpp: ref_gpuserver_query) -> (ids, scores)"""
+        q = np.ascontiguousarray(q, np.uint8); prof = np.ascontiguousarray(profile, np.int8)
+        ids = np.zeros(cap, np.uint32); sc = np.zeros(cap, np.int32)
+        self.lib.ref_gpuserver_query.restype = ctypes.c_int64
+        n = self.lib.ref_gpuserver_query(shm_name.encode(), _p(q), len(q), _p(prof), prof.shape[0], _p(ids), _p(sc), ctypes.c_int64(cap))
+        if n < 0:
+            raise RuntimeError("server exited")
+        return ids[:n].copy(), sc[:n].copy()
+
     def result_to_buffer(self, db_key, score, seq_id, evalue, qs, qe, ql, ds, de, dl, backtrace=b"", add_backtrace=False, compress=True):
         out = ctypes.create_string_buffer(1024 + 2 * len(backtrace))
         self.lib.ref_result_to_buffer.restype = ctypes.c_int64

@@ -43,6 +43,9 @@
 #include "Matcher.h"
 #include "DBReader.h"
 #include "DBWriter.h"
+#include "GpuUtil.h"
+#include "PrefilteringIndexReader.h"
+#include <thread>
 #include "QueryMatcher.h"
 #include "ProfileStates.h"
 #include "Util.h"
@@ -50,7 +53,11 @@
 #include "block_aligner.h"
 #include "ksw2.h"
 
+const char *version = "b200-pinning-harness";   // the reference binary's version string (GpuUtil.cpp:16 uses it in the shm name hash)
+
 // ---------------------------------------------------------------- link-time stand-ins
+// only GPUSharedMemory::getShmHash calls it (shm name from the DB path); the harness passes explicit names
+std::string PrefilteringIndexReader::dbPathWithoutIndex(const std::string &dbname) { return dbname; }
 ProfileStates::ProfileStates(int, double *) { abort(); }
 ProfileStates::~ProfileStates() {}
 
@@ -669,6 +676,46 @@ int64_t ref_db_read(const char *path, uint32_t *keys, int64_t *lens, char *data,
     *used = u;
     *dbtype = r.getDbtype();
     r.close();
+    return n;
+}
+
+// ---- gpuserver protocol, client side: GPUSharedMemory::openSharedMemory (GpuUtil.cpp:91-120, the reference's own code) and the
+// request state machine of ungappedprefilter.cpp:209-250 (IDLE -> RESERVED -> READY ... DONE -> IDLE), restated around it.
+// profile: [alphabetSize][qL] int8 as ungappedprefilter.cpp:195-203 builds it.  Returns the number of results (-1: server exited).
+int64_t ref_gpuserver_query(const char *shmName, const unsigned char *q, int qL, const int8_t *profile, int alphabetSize,
+                            uint32_t *ids, int32_t *scores, int64_t cap) {
+    GPUSharedMemory *layout = GPUSharedMemory::openSharedMemory(shmName);
+    int64_t n = -1;
+    bool claimed = false;
+    while (!claimed) {
+        if (layout->serverExit.load(std::memory_order_acquire) == true) break;
+        int expected = GPUSharedMemory::IDLE;
+        int desired = GPUSharedMemory::RESERVED;
+        if (layout->state.compare_exchange_strong(expected, desired, std::memory_order_acq_rel)) {
+            claimed = true;
+            memcpy(layout->getQueryPtr(), q, qL);
+            memcpy(layout->getProfilePtr(), profile, (size_t) alphabetSize * qL);
+            layout->queryLen = qL;
+            std::atomic_thread_fence(std::memory_order_release);
+            layout->state.store(GPUSharedMemory::READY, std::memory_order_release);
+            bool done = false;
+            while (true) {
+                if (layout->serverExit.load(std::memory_order_acquire) == true) break;
+                if (layout->state.load(std::memory_order_acquire) == GPUSharedMemory::DONE) { done = true; break; }
+                std::this_thread::yield();
+            }
+            if (done) {
+                std::atomic_thread_fence(std::memory_order_acquire);
+                n = layout->resultLen;
+                Marv::Result *r = layout->getResultsPtr();
+                for (int64_t i = 0; i < n && i < cap; i++) { ids[i] = r[i].id; scores[i] = r[i].score; }
+                layout->state.store(GPUSharedMemory::IDLE, std::memory_order_release);
+            }
+        } else {
+            std::this_thread::yield();
+        }
+    }
+    GPUSharedMemory::unmap(layout);
     return n;
 }
 
