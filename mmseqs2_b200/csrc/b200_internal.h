@@ -44,7 +44,7 @@ struct DevPool {
     }
     void give(void *p, size_t cap, int dev) {
         std::lock_guard<std::mutex> lk(mu);
-        if (free_list.size() >= 64 || held + cap > ((size_t) 8 << 30)) { cudaFree(p); return; }
+        if (free_list.size() >= 256 || held + cap > ((size_t) 32 << 30)) { cudaFree(p); return; }   // of 180 GB HBM
         Slot s = {p, cap, dev};
         free_list.push_back(s);
         held += cap;
