@@ -72,3 +72,32 @@ def test_gap_penalty_variants(ref, oracle, blosum):
         assert np.array_equal(ref.sw_score_endpos(q, True, td, to, go, ge), oracle.sw_score_endpos(q, cb, bias, td, to, go, ge))
         a, _, _ = ref.ssw_align(q, True, td, to, go, ge, mode=1)
         assert np.array_equal(a[:, :6], oracle.sw_align(q, cb, bias, td, to, go, ge))
+
+
+def test_backtrace_gap_penalty_variants_and_wide_bands(ref, oracle, blosum):
+    """banded_sw + computerBacktrace of the reference (ssw_align mode 2) against the restatement for gap costs with go > ge,
+    go == ge, go < ge and for alignments whose band doubles far beyond |dbLen - qLen| + 1 -- the cases the GPU parity test of the
+    warp backtrace kernel (tests/test_gpu_parity.py::test_backtrace_gap_penalties_and_wide_bands) checks against the oracle"""
+    rng = np.random.default_rng(4242)
+    bg = synth.background(blosum[1])
+    q = synth.random_seqs(rng, 1, bg, mean=600, sigma=0, lo=600, hi=600, normal=True)[0]
+    tg = [synth.mutate(rng, q, bg, s, i) for s, i in ((0.1, 0.02), (0.3, 0.05), (0.2, 0.0), (0.05, 0.1), (0.4, 0.03))]
+    tg.append(np.concatenate([q[:200], q[420:]]))
+    tg.append(np.concatenate([q[:100], synth.random_seqs(rng, 1, bg, mean=300, sigma=0, lo=300, hi=300, normal=True)[0], q[100:]]))
+    tg.append(q[50:550].copy())
+    tg += [synth.mutate(rng, q[a:a + 250], bg, 0.25, 0.04) for a in (0, 100, 350)]
+    td, to = pack_targets(tg)
+    cb, bias = oracle.query_cb(q, True)
+    checked = 0
+    for go, ge in ((11, 1), (5, 2), (3, 3), (2, 4), (20, 1)):
+        a, _, bts = ref.ssw_align(q, True, td, to, go, ge, mode=2, want_bt=True)
+        exp = oracle.sw_align(q, cb, bias, td, to, go, ge)
+        assert np.array_equal(a[:, :6], exp), (go, ge)
+        for k in range(len(tg)):
+            if exp[k, 4] == -1:
+                continue
+            bt, ids = oracle.backtrace(q, cb, tg[k], exp[k], go, ge)
+            assert bt == bts[k] and ids == a[k, 6], (go, ge, k)
+            checked += 1
+    assert checked >= 40
+
