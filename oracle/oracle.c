@@ -379,3 +379,78 @@ int orc_sw_backtrace(const int16_t *mat, int A, const uint8_t *q, const int8_t *
     free(c); free(direction); free(hb); free(eb); free(hc);
     return len;
 }
+
+/* ---- SURVEY 8f row 3 groundwork: DistanceCalculator::computeUngappedAlignment on ASCII sequences -------------------
+ * (src/alignment/DistanceCalculator.h:93-174, the per-mode scorers :15-37,177-271, DistanceCalculator.cpp:5-25), as
+ * rescorediagonal (src/alignment/rescorediagonal.cpp:231-236) and BandedNucleotideAligner (:104-107) call it.
+ * asciimat: [123][123] scores indexed by the two characters (SubstitutionMatrix::createAsciiSubMat).
+ * out = {score, startPos, endPos, diagonalLen, distToDiagonal, diagonal}.  No device counterpart yet (next round). */
+static void orc_rescore_one(const char *q, unsigned qL, const char *t, unsigned tL, int diagonal, const int8_t *m, int mode, int64_t out[6]) {
+    const unsigned dist = (unsigned) (diagonal < 0 ? -diagonal : diagonal);
+    out[0] = 0; out[1] = -1; out[2] = -1; out[3] = 0; out[4] = dist; out[5] = diagonal;
+    const char *a, *b;
+    unsigned len;
+    if (diagonal >= 0 && dist < qL) { len = tL < qL - dist ? tL : qL - dist; a = q + dist; b = t; }
+    else if (diagonal < 0 && dist < tL) { len = tL - dist < qL ? tL - dist : qL; a = q; b = t + dist; }
+    else return;
+    out[3] = len;
+#define SC(i) ((int) m[(size_t) (unsigned char) a[i] * 123 + (unsigned char) b[i]])
+    if (mode == 0) {                       /* HAMMING: number of equal characters */
+        unsigned same = 0;
+        for (unsigned i = 0; i < len; i++) same += a[i] == b[i];
+        out[0] = same;
+    } else if (mode == 1) {                /* SUBSTITUTION: best 0-reset running sum */
+        int best = 0, s = 0;
+        for (unsigned i = 0; i < len; i++) { s += SC(i); if (s < 0) s = 0; if (s > best) best = s; }
+        out[0] = best;
+    } else if (mode == 2) {                /* ALIGNMENT: the same with the segment that attains it (first maximum) */
+        int best = 0, s = 0, minPos = -1, st = 0, en = 0;
+        for (unsigned i = 0; i < len; i++) {
+            s += SC(i);
+            if (s <= 0) { s = 0; minPos = (int) i; }
+            if (s > best) { best = s; en = (int) i; st = minPos + 1; }
+        }
+        out[0] = best; out[1] = st; out[2] = en;
+    } else if (mode == 3) {                /* END_TO_END: whole diagonal, '*' at either end skipped, floor 0 */
+        unsigned first = (a[0] == '*' || b[0] == '*') ? 1 : 0, last = len - 1;
+        if (last > 0 && (a[len - 1] == '*' || b[len - 1] == '*')) last--;
+        int64_t s = 0;
+        for (unsigned i = first; i <= last; i++) s += SC(i);
+        out[0] = s > 0 ? s : 0; out[1] = first; out[2] = last;
+    } else {                               /* WINDOW_QUALITY: longest stretch with <= 5 mismatches in any window of 20 */
+        const unsigned W = 20, E = 5;
+        uint64_t window = 0;
+        const uint64_t mask = (uint64_t) 1 << (W - 1);
+        unsigned errs = 0, maxLen = 0, curLen = 0, maxEnd = 0, maxStart = 0;
+        unsigned first = (a[0] == '*' || b[0] == '*') ? 1 : 0, last = len - 1;
+        if (last > 0 && (a[len - 1] == '*' || b[len - 1] == '*')) last--;
+        unsigned start = first;
+        for (unsigned i = first; i <= last; i++) {
+            const int match = a[i] == b[i];
+            if (window & mask) errs -= 1;
+            window <<= 1;
+            if (!match) { window |= 1; errs += 1; }
+            curLen += 1;
+            if (i >= W - 1 && errs > E) { start = i - W + 2; curLen = W - 1; }
+            if (curLen > maxLen) { maxStart = start; maxEnd = i; maxLen = curLen; }
+        }
+        int s = 0;
+        for (unsigned i = maxStart; i < maxEnd; i++) s += SC(i);
+        out[0] = (unsigned) s; out[1] = maxStart; out[2] = maxEnd;
+    }
+#undef SC
+}
+
+void orc_rescore_diagonal(const char *q, int qL, const char *t, int tL, uint16_t diagonal, const int8_t *asciimat, int mode, int64_t out[6]) {
+    int64_t best[6] = {0, -1, -1, 0, 0, 0}, cur[6];
+    /* the unsigned short diagonal stands for every real diagonal congruent to it mod 65536 that meets the rectangle (:98-112) */
+    for (unsigned d = 1; d <= 1 + (unsigned) tL / 32768; d++) {
+        orc_rescore_one(q, (unsigned) qL, t, (unsigned) tL, -(int) (d * 65536) + (int) diagonal, asciimat, mode, cur);
+        if ((uint32_t) cur[0] > (uint32_t) best[0]) for (int k = 0; k < 6; k++) best[k] = cur[k];
+    }
+    for (unsigned d = 0; d <= (unsigned) qL / 65536; d++) {
+        orc_rescore_one(q, (unsigned) qL, t, (unsigned) tL, (int) (d * 65536) + (int) diagonal, asciimat, mode, cur);
+        if ((uint32_t) cur[0] > (uint32_t) best[0]) for (int k = 0; k < 6; k++) best[k] = cur[k];
+    }
+    for (int k = 0; k < 6; k++) out[k] = best[k];
+}

@@ -110,6 +110,13 @@ class Oracle:
                                       int(aln[0]), go, ge, buf, len(buf), ctypes.byref(ids))
         return (buf.value.decode() if n >= 0 else None), ids.value
 
+    def rescore_diagonal(self, q_ascii, t_ascii, diagonal_u16, asciimat, mode):
+        """DistanceCalculator::computeUngappedAlignment restated (8f row 3 groundwork) -> 6 fields"""
+        out = np.zeros(6, np.int64)
+        self.lib.orc_rescore_diagonal(q_ascii, len(q_ascii), t_ascii, len(t_ascii), ctypes.c_uint16(diagonal_u16 & 0xffff), _p(asciimat), mode,
+                                      _p(out))
+        return out
+
     def diag(self, q, cb4, tdata, toff, hit_ids, hit_diags):
         q = np.ascontiguousarray(q, np.uint8)
         ids = np.ascontiguousarray(hit_ids, np.uint32)
@@ -256,6 +263,16 @@ class Ref:
         if n < 0:
             raise RuntimeError("server exited")
         return ids[:n].copy(), sc[:n].copy()
+
+    def ascii_matrix(self):
+        m = np.zeros((123, 123), np.int8)
+        self.lib.ref_rescore_diagonal(None, 0, None, 0, ctypes.c_uint16(0), 0, None, _p(m))
+        return m
+
+    def rescore_diagonal(self, q_ascii, t_ascii, diagonal_u16, mode):
+        out = np.zeros(6, np.int64)
+        self.lib.ref_rescore_diagonal(q_ascii, len(q_ascii), t_ascii, len(t_ascii), ctypes.c_uint16(diagonal_u16 & 0xffff), mode, _p(out), None)
+        return out
 
     def result_to_buffer(self, db_key, score, seq_id, evalue, qs, qe, ql, ds, de, dl, backtrace=b"", add_backtrace=False, compress=True):
         out = ctypes.create_string_buffer(1024 + 2 * len(backtrace))

@@ -41,6 +41,7 @@
 #include "EvalueComputation.h"
 #include "BandedNucleotideAligner.h"
 #include "Matcher.h"
+#include "DistanceCalculator.h"
 #include "DBReader.h"
 #include "DBWriter.h"
 #include "GpuUtil.h"
@@ -717,6 +718,18 @@ int64_t ref_gpuserver_query(const char *shmName, const unsigned char *q, int qL,
     }
     GPUSharedMemory::unmap(layout);
     return n;
+}
+
+// ---- SURVEY 8f row 3 groundwork: DistanceCalculator::computeUngappedAlignment on ASCII sequences with the amino-acid fast matrix
+// out = score, startPos, endPos, diagonalLen, distToDiagonal, diagonal; asciimat (may be NULL) receives the [123][123] table
+void ref_rescore_diagonal(const char *q, int qL, const char *t, int tL, uint16_t diagonal, int mode, int64_t *out, int8_t *asciimat) {
+    static SubstitutionMatrix::FastMatrix fast = SubstitutionMatrix::createAsciiSubMat(*g_aa);
+    if (asciimat != NULL)
+        for (int i = 0; i < 123; i++)
+            for (int j = 0; j < 123; j++) asciimat[i * 123 + j] = (int8_t) fast.matrix[i][j];
+    if (q == NULL) return;
+    DistanceCalculator::LocalAlignment r = DistanceCalculator::computeUngappedAlignment(q, (unsigned) qL, t, (unsigned) tL, diagonal, fast.matrix, mode);
+    out[0] = r.score; out[1] = r.startPos; out[2] = r.endPos; out[3] = r.diagonalLen; out[4] = r.distToDiagonal; out[5] = r.diagonal;
 }
 
 }  // extern "C"

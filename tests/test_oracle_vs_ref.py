@@ -101,3 +101,29 @@ def test_backtrace_gap_penalty_variants_and_wide_bands(ref, oracle, blosum):
             checked += 1
     assert checked >= 40
 
+
+def test_rescore_diagonal_modes(ref, oracle):
+    """groundwork for SURVEY 8f row 3 (no device path yet): the restatement of DistanceCalculator::computeUngappedAlignment equals
+    the reference for all five rescore modes on ASCII sequences with lower case, ambiguity letters and '*' ends"""
+    rng = np.random.default_rng(31337)
+    m = ref.ascii_matrix()
+    letters = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWYXBZUacdklmn", np.uint8)
+    checked = 0
+    for rep in range(300):
+        qL, tL = int(rng.integers(1, 400)), int(rng.integers(1, 400))
+        q = bytearray(rng.choice(letters, qL).tobytes()); t = bytearray(rng.choice(letters, tL).tobytes())
+        if rep % 3 == 0:                                   # a shared segment so that the scores are not all tiny
+            n = int(rng.integers(1, min(qL, tL) + 1)); a = int(rng.integers(0, qL - n + 1)); b = int(rng.integers(0, tL - n + 1))
+            t[b:b + n] = q[a:a + n]
+            for k in rng.integers(0, n, n // 8):
+                t[b + int(k)] = int(rng.choice(letters))
+        if rep % 5 == 0:
+            q[0] = ord("*"); t[-1] = ord("*")
+        for diag in [0, 1, -1 & 0xffff, int(rng.integers(-tL, qL + 1)) & 0xffff, int(rng.integers(-tL, qL + 1)) & 0xffff, 5000, 60000]:
+            for mode in range(5):
+                exp = ref.rescore_diagonal(bytes(q), bytes(t), diag, mode)
+                got = oracle.rescore_diagonal(bytes(q), bytes(t), diag, m, mode)
+                assert np.array_equal(got, exp), (rep, diag, mode, got, exp)
+                checked += 1
+    assert checked == 300 * 7 * 5
+
