@@ -75,9 +75,12 @@ def test_gap_penalty_variants(ref, oracle, blosum):
 
 
 def test_backtrace_gap_penalty_variants_and_wide_bands(ref, oracle, blosum):
-    """banded_sw + computerBacktrace of the reference (ssw_align mode 2) against the restatement for gap costs with go > ge,
-    go == ge, go < ge and for alignments whose band doubles far beyond |dbLen - qLen| + 1 -- the cases the GPU parity test of the
-    warp backtrace kernel (tests/test_gpu_parity.py::test_backtrace_gap_penalties_and_wide_bands) checks against the oracle"""
+    """banded_sw + computerBacktrace of the reference (ssw_align mode 2) against the restatement for several gap costs and for
+    alignments whose band doubles far beyond |dbLen - qLen| + 1 -- the cases the GPU parity test of the warp backtrace kernel
+    (tests/test_gpu_parity.py::test_backtrace_gap_penalties_and_wide_bands) checks against the oracle.
+    Only go > ge: with go <= ge the reference's striped kernels stop being the Gotoh recurrence (on the 220-residue deletion below
+    its forward pass scores 1316, its own reverse pass 1321, the textbook DP 1329, and ssw_align exits on its forward/backward
+    check) -- there is no reference behaviour to pin there; the library and the oracle compute the textbook recurrence."""
     rng = np.random.default_rng(4242)
     bg = synth.background(blosum[1])
     q = synth.random_seqs(rng, 1, bg, mean=600, sigma=0, lo=600, hi=600, normal=True)[0]
@@ -89,7 +92,7 @@ def test_backtrace_gap_penalty_variants_and_wide_bands(ref, oracle, blosum):
     td, to = pack_targets(tg)
     cb, bias = oracle.query_cb(q, True)
     checked = 0
-    for go, ge in ((11, 1), (5, 2), (3, 3), (2, 4), (20, 1)):
+    for go, ge in ((11, 1), (5, 2), (20, 1), (10, 2), (4, 3)):
         a, _, bts = ref.ssw_align(q, True, td, to, go, ge, mode=2, want_bt=True)
         exp = oracle.sw_align(q, cb, bias, td, to, go, ge)
         assert np.array_equal(a[:, :6], exp), (go, ge)
