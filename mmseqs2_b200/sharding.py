@@ -46,3 +46,28 @@ def gather_hit_lists(hits, n_hits, max_queries_per_rank, dist=None, device=None)
     hb = flat[:, :buf.size].reshape(world, max_queries_per_rank, k, 2)
     cn = flat[:, buf.size:]
     return hb, cn
+
+
+def merge_target_sharded(hits, n_hits, id_offset, k, dist=None, device=None):
+    """The other split of SURVEY 8e, for a DB too large for one GPU: every rank holds a slice of the TARGETS (its local ids start
+    at id_offset in the global numbering) and has scanned all queries against it.  hits [nq][k_local] / n_hits [nq] are the local
+    top lists; the result on every rank is the global top-k per query, ordered like hit_t::compareHitsByScoreAndId (score desc,
+    global id asc) -- the deterministic tie-break that makes the merged list independent of the number of ranks.
+    One all_gather of fixed-size records, then a k-way merge (here: one sort of world * k_local records per query)."""
+    nq = hits.shape[0]
+    local = hits.copy()
+    for i in range(nq):
+        local["id"][i, :int(n_hits[i])] += np.uint32(id_offset)
+    hb, cn = gather_hit_lists(local, n_hits, nq, dist, device)
+    world = hb.shape[0]
+    out = np.zeros((nq, k), hits.dtype)
+    n_out = np.zeros(nq, np.uint32)
+    for i in range(nq):
+        ids = np.concatenate([hb[r, i, :int(cn[r, i]), 0] for r in range(world)]).view(np.uint32) if world else np.zeros(0, np.uint32)
+        sc = np.concatenate([hb[r, i, :int(cn[r, i]), 1] for r in range(world)]) if world else np.zeros(0, np.int32)
+        order = np.lexsort((ids, -sc.astype(np.int64)))[:k]
+        n_out[i] = len(order)
+        out["id"][i, :len(order)] = ids[order]
+        out["score"][i, :len(order)] = sc[order]
+    return out, n_out
+

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from mmseqs2_b200.sharding import decompose_by_residues, gather_hit_lists
+from mmseqs2_b200.sharding import decompose_by_residues, gather_hit_lists, merge_target_sharded
 
 K = 7
 HIT = np.dtype([("id", np.uint32), ("score", np.int32)])
@@ -75,3 +75,54 @@ def test_two_rank_gather_equals_single_process():
     for q in range(len(qlens)):
         exp = hits[q, :n[q]].view(np.int32).reshape(-1, 2).tolist()
         assert merged[q] == exp
+
+
+# ---- target-sharded variant: each rank scans its slice of the DB, the top lists are merged ---------------------------------------
+def _dense_scores(nq, n_targets):
+    rng = np.random.default_rng(123)
+    return rng.integers(0, 40, (nq, n_targets)).astype(np.int32)      # few distinct values: plenty of ties at the cut-off
+
+
+def _topk(dense_row, ids, k, thr=15):
+    sel = np.nonzero(dense_row > thr)[0]
+    order = sel[np.lexsort((ids[sel], -dense_row[sel].astype(np.int64)))][:k]
+    return ids[order], dense_row[order]
+
+
+def _merge_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nq, nt, k = 6, 500, 20
+    dense = _dense_scores(nq, nt)
+    lo, hi = (0, 230) if rank == 0 else (230, nt)                       # uneven slices
+    hits = np.zeros((nq, k), HIT)
+    n = np.zeros(nq, np.uint32)
+    for i in range(nq):
+        ids, sc = _topk(dense[i, lo:hi], np.arange(hi - lo, dtype=np.uint32), k)
+        n[i] = len(ids); hits["id"][i, :len(ids)] = ids; hits["score"][i, :len(ids)] = sc
+    merged, nm = merge_target_sharded(hits, n, lo, k, dist)
+    if rank == 1:
+        ret.put((merged.tolist(), nm.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_target_sharded_merge_equals_unsharded_topk():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_merge_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    merged, nm = ret.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    nq, nt, k = 6, 500, 20
+    dense = _dense_scores(nq, nt)
+    for i in range(nq):
+        ids, sc = _topk(dense[i], np.arange(nt, dtype=np.uint32), k)
+        assert nm[i] == len(ids)
+        assert [m[0] for m in merged[i][:nm[i]]] == ids.tolist() and [m[1] for m in merged[i][:nm[i]]] == sc.tolist()
+
