@@ -62,6 +62,7 @@ typedef struct { int32_t score, qend, dbend, word; } b200_sw_end;        /* s_al
 typedef struct { int32_t score, qstart, qend, dbstart, dbend, word; } b200_sw_aln;
 
 /* ---- context -------------------------------------------------------------------------------- */
+int b200_device_count(void);                       /* Marv::getDeviceIds (marv.h:19) */
 int b200_create(int device, b200_ctx **ctx);
 void b200_destroy(b200_ctx *ctx);
 const char *b200_last_error(const b200_ctx *ctx);
@@ -78,6 +79,11 @@ float b200_last_kernel_ms(const b200_ctx *ctx);
 /* ---- target DB ------------------------------------------------------------------------------- */
 /* residues: numeric codes 0..alphabet-1, sequence i = residues[offsets[i] .. offsets[i+1]).  Copied to HBM. */
 int b200_db_load(b200_ctx *ctx, const uint8_t *residues, const uint64_t *offsets, uint64_t n_seq, int alphabet);
+/* The same from the padded GPU DB of `makepaddedseqdb` as Marv::loadDb takes it (lib/libmarv/src/marv.h:20; layout
+ * src/util/makepaddedseqdb.cpp:66-98; offsets/lengths as src/prefiltering/ungappedprefilter.cpp:127-139 builds them): sequence i =
+ * data[offsets[i] .. offsets[i] + lengths[i]), numeric codes with +32 marking soft-masked residues, which become X = alphabet-1 as
+ * in the CPU scorer (ungappedprefilter.cpp:401-404). */
+int b200_db_load_padded(b200_ctx *ctx, const uint8_t *data, const size_t *offsets, const int32_t *lengths, uint64_t n_seq, int alphabet);
 uint64_t b200_db_num_seqs(const b200_ctx *ctx);
 uint64_t b200_db_num_residues(const b200_ctx *ctx);
 

@@ -32,6 +32,11 @@ int b200h_build_profile(const int16_t *mat, int A, const uint8_t *q, int L, cons
  * profile bias |min(0, min pssm)| (no composition bias in the profile branch), or -1 (B200_ERR_ARG) on bad sizes. */
 int b200h_build_profile_pssm(const int8_t *pssm, int rows, int L, int A, int8_t *out);
 
+/* SSW profile bias recovered from (encoded query, [A][L] profile, matrix) -- what Marv::scan (lib/libmarv/src/marv.h:47) and the
+ * gpuserver protocol (src/commons/GpuUtil.h) carry.  mat may be NULL (then, or when profile - matrix is not one composition bias per
+ * column, the profile-query rule applies: |min(0, lowest entry of the first A-1 rows)|). */
+int b200h_ssw_bias_from_profile(const int16_t *mat, int A, const uint8_t *q, int L, const int8_t *profile);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@
 #include <mutex>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 struct QueryDesc {     // device-side description of one query profile
@@ -1166,54 +1167,111 @@ int b200_sync(b200_ctx *ctx) {
 }
 
 // ---- DB -------------------------------------------------------------------------------------------
+// Common body of b200_db_load / b200_db_load_padded.  src(i) = first residue of sequence i, len[i] its length; bytes >= mask_from
+// (the +32 soft-mask bit of the padded GPU DB, makepaddedseqdb.cpp:77-86) become X = alphabet-1, as runFilterOnCpu treats masked
+// residues (ungappedprefilter.cpp:401-404); mask_from = 256 disables that.  The re-layout (16-byte aligned, padded with code
+// `alphabet`) runs on all host threads: at 20 M sequences this is 7.5 GB of bytes.
+static int db_load_impl(b200_ctx *ctx, const uint8_t *base, const uint64_t *starts, const int32_t *lens, uint64_t n_seq, int alphabet,
+                        int mask_from, uint64_t n_res) {
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    db_free(ctx);
+    std::vector<uint64_t> h_off(n_seq);
+    ctx->h_len.assign(lens, lens + n_seq);
+    uint64_t total = 0;
+    int max_len = 0;
+    for (uint64_t i = 0; i < n_seq; i++) {
+        h_off[i] = total;
+        max_len = std::max(max_len, (int) lens[i]);
+        total += round_up((uint64_t) lens[i], 16);
+    }
+    total += 32;
+    uint8_t *h_res = nullptr;
+    CU_TRY(ctx, cudaMallocHost(&h_res, total));
+    const unsigned nt = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+    std::vector<int> bad(nt, 0);
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++)
+            th.emplace_back([&, t]() {
+                const uint64_t i0 = n_seq * t / nt, i1 = n_seq * (t + 1) / nt;
+                const uint64_t b0 = i0 < n_seq ? h_off[i0] : total - 32, b1 = i1 < n_seq ? h_off[i1] : total;
+                memset(h_res + b0, alphabet, b1 - b0);
+                for (uint64_t i = i0; i < i1; i++) {
+                    const uint8_t *src = base + starts[i];
+                    uint8_t *dst = h_res + h_off[i];
+                    for (int32_t j = 0; j < lens[i]; j++) {
+                        uint8_t c = src[j];
+                        if (c >= mask_from) c = (uint8_t) (alphabet - 1);
+                        if (c >= alphabet) bad[t] = 1;
+                        dst[j] = c;
+                    }
+                }
+            });
+        for (auto &x : th) x.join();
+    }
+    for (unsigned t = 0; t < nt; t++)
+        if (bad[t]) { cudaFreeHost(h_res); return set_err(ctx, B200_ERR_ARG, "b200_db_load: residue code >= alphabet (strip the +32 mask bit first)"); }
+    std::vector<uint32_t> order(n_seq);
+    std::iota(order.begin(), order.end(), 0u);
+    const int32_t *hl = ctx->h_len.data();
+    std::stable_sort(order.begin(), order.end(), [hl](uint32_t a, uint32_t b) { return hl[a] > hl[b]; });
+    cudaError_t e = cudaMalloc(&ctx->d_res, total);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_off, n_seq * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_len, n_seq * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_order, n_seq * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_res, h_res, total, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_off, h_off.data(), n_seq * sizeof(uint64_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_len, ctx->h_len.data(), n_seq * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(ctx->d_order, order.data(), n_seq * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    cudaFreeHost(h_res);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("b200_db_load: ") + cudaGetErrorString(e);
+        db_free(ctx);
+        return e == cudaErrorMemoryAllocation ? B200_ERR_NOMEM : B200_ERR_CUDA;
+    }
+    ctx->n_seq = n_seq;
+    ctx->n_res = n_res;
+    ctx->alphabet = alphabet;
+    ctx->max_len = max_len;
+    return B200_OK;
+}
+
 int b200_db_load(b200_ctx *ctx, const uint8_t *residues, const uint64_t *offsets, uint64_t n_seq, int alphabet) {
     if (ctx == nullptr) return B200_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (residues == nullptr || offsets == nullptr || n_seq == 0 || alphabet <= 0 || alphabet > 31)
         return set_err(ctx, B200_ERR_ARG, "b200_db_load: bad arguments");
     if (n_seq >= 0xffffffffull) return set_err(ctx, B200_ERR_RANGE, "b200_db_load: more than 2^32-1 sequences");
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
-    db_free(ctx);
-    std::vector<uint64_t> h_off(n_seq);
-    ctx->h_len.resize(n_seq);
-    uint64_t total = 0;
-    int max_len = 0;
+    std::vector<int32_t> lens(n_seq);
     for (uint64_t i = 0; i < n_seq; i++) {
         if (offsets[i + 1] < offsets[i]) return set_err(ctx, B200_ERR_ARG, "b200_db_load: offsets not monotone");
         const uint64_t l = offsets[i + 1] - offsets[i];
         if (l > 65535) return set_err(ctx, B200_ERR_RANGE, "b200_db_load: sequence longer than 65535 (maxSeqLen)");
-        h_off[i] = total;
-        ctx->h_len[i] = (int32_t) l;
-        max_len = std::max(max_len, (int) l);
-        total += round_up(l, 16);
+        lens[i] = (int32_t) l;
     }
-    total += 32;
-    std::vector<uint8_t> h_res(total, (uint8_t) alphabet);
+    return db_load_impl(ctx, residues, offsets, lens.data(), n_seq, alphabet, 256, offsets[n_seq] - offsets[0]);
+}
+
+int b200_db_load_padded(b200_ctx *ctx, const uint8_t *data, const size_t *offsets, const int32_t *lengths, uint64_t n_seq, int alphabet) {
+    if (ctx == nullptr) return B200_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (data == nullptr || offsets == nullptr || lengths == nullptr || n_seq == 0 || alphabet <= 0 || alphabet > 31)
+        return set_err(ctx, B200_ERR_ARG, "b200_db_load_padded: bad arguments");
+    if (n_seq >= 0xffffffffull) return set_err(ctx, B200_ERR_RANGE, "b200_db_load_padded: more than 2^32-1 sequences");
+    std::vector<uint64_t> starts(n_seq);
+    uint64_t n_res = 0;
     for (uint64_t i = 0; i < n_seq; i++) {
-        const uint8_t *src = residues + offsets[i];
-        uint8_t *dst = h_res.data() + h_off[i];
-        for (int32_t j = 0; j < ctx->h_len[i]; j++) {
-            if (src[j] >= alphabet) return set_err(ctx, B200_ERR_ARG, "b200_db_load: residue code >= alphabet (strip the +32 mask bit first)");
-            dst[j] = src[j];
-        }
+        if (lengths[i] < 0 || lengths[i] > 65535) return set_err(ctx, B200_ERR_RANGE, "b200_db_load_padded: sequence length outside [0,65535]");
+        starts[i] = offsets[i];
+        n_res += (uint64_t) lengths[i];
     }
-    std::vector<uint32_t> order(n_seq);
-    std::iota(order.begin(), order.end(), 0u);
-    const int32_t *hl = ctx->h_len.data();
-    std::stable_sort(order.begin(), order.end(), [hl](uint32_t a, uint32_t b) { return hl[a] > hl[b]; });
-    CU_TRY(ctx, cudaMalloc(&ctx->d_res, total));
-    CU_TRY(ctx, cudaMalloc(&ctx->d_off, n_seq * sizeof(uint64_t)));
-    CU_TRY(ctx, cudaMalloc(&ctx->d_len, n_seq * sizeof(int32_t)));
-    CU_TRY(ctx, cudaMalloc(&ctx->d_order, n_seq * sizeof(uint32_t)));
-    CU_TRY(ctx, cudaMemcpy(ctx->d_res, h_res.data(), total, cudaMemcpyHostToDevice));
-    CU_TRY(ctx, cudaMemcpy(ctx->d_off, h_off.data(), n_seq * sizeof(uint64_t), cudaMemcpyHostToDevice));
-    CU_TRY(ctx, cudaMemcpy(ctx->d_len, ctx->h_len.data(), n_seq * sizeof(int32_t), cudaMemcpyHostToDevice));
-    CU_TRY(ctx, cudaMemcpy(ctx->d_order, order.data(), n_seq * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    ctx->n_seq = n_seq;
-    ctx->n_res = offsets[n_seq] - offsets[0];
-    ctx->alphabet = alphabet;
-    ctx->max_len = max_len;
-    return B200_OK;
+    return db_load_impl(ctx, data, starts.data(), lengths, n_seq, alphabet, 32, n_res);
+}
+
+int b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
 }
 
 uint64_t b200_db_num_seqs(const b200_ctx *ctx) { return ctx ? ctx->n_seq : 0; }

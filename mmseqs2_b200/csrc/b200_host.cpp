@@ -73,4 +73,30 @@ int b200h_build_profile_pssm(const int8_t *pssm, int rows, int L, int A, int8_t 
     return lowest < 0 ? -lowest : lowest;
 }
 
+// The SSW profile bias from what Marv::scan / the gpuserver protocol carry: the encoded query, its [A][L] profile and (optionally) the
+// substitution matrix.  A sequence query's profile is mat[a][q[j]] + cb[j] (ungappedprefilter.cpp:195-203), so profile - matrix column
+// is the same rounded composition bias in every residue row, and the bias is ssw_init's |min(mat)| + |min(0, min cb)|
+// (StripedSmithWaterman.cpp:1375-1406).  Anything else is a profile (HMM) query, whose bias is |min(0, lowest entry)| with the X row
+// counted as 0 (the isProfile branch, :1388-1406; the caller's table is the alignment profile itself).
+int b200h_ssw_bias_from_profile(const int16_t *mat, int A, const uint8_t *q, int L, const int8_t *profile) {
+    if (profile == nullptr || L <= 0 || A <= 0) return 0;
+    bool is_seq = mat != nullptr && q != nullptr;
+    int comp = 0;
+    for (int j = 0; j < L && is_seq; j++) {
+        if (q[j] >= A) { is_seq = false; break; }
+        const int d = (int) profile[j] - (int) mat[q[j]];
+        for (int a = 1; a < A; a++)
+            if ((int) profile[(size_t) a * L + j] - (int) mat[(size_t) a * A + q[j]] != d) { is_seq = false; break; }
+        comp = std::min(comp, d);
+    }
+    if (is_seq) {
+        int bias = 0;
+        for (int i = 0; i < A * A; i++) bias = std::min(bias, (int) (int8_t) mat[i]);
+        return std::abs(bias) + std::abs(comp);
+    }
+    int lowest = 0;
+    for (size_t i = 0; i < (size_t) (A - 1) * L; i++) lowest = std::min(lowest, (int) profile[i]);
+    return -lowest;
+}
+
 }  // extern "C"
