@@ -140,32 +140,116 @@ def measured_int_peak():
         return {}, "microbenchmark unavailable: %r" % (e,)
 
 
-def cpu_reference_gcups(queries, res, off, budget_s, threads):
-    """the reference's ungapped_alignment (oracle/_ref) or the C port on the host cores: whole-DB passes of successive
-    queries of the same workload until `budget_s` seconds have been spent (bounded sample)"""
-    from oracle.pyoracle import Oracle, Ref
-    mat, pb = load_matrix()
-    off64 = off.astype(np.int64)
-    use_ref = Ref.available()
-    ref = Ref() if use_ref else None
-    orc = None if use_ref else Oracle(mat, pb)
-    n_warm = min(len(off64) - 1, 2000)
-    if use_ref:
-        ref.ungapped(queries[0], True, res[:int(off64[n_warm])], off64[:n_warm + 1], nthreads=threads)
-    cells, dt, nq = 0.0, 0.0, 0
-    while dt < budget_s and nq < len(queries):
-        q = queries[nq]
-        t0 = time.perf_counter()
-        if use_ref:
-            ref.ungapped(q, True, res, off64, nthreads=threads)
+def cpu_info():
+    """what the host really offers: affinity mask, cgroup quota, model -- os.cpu_count() alone overstates a restricted box"""
+    info = {"os_cpu_count": os.cpu_count(), "affinity_cpus": len(os.sched_getaffinity(0))}
+    try:
+        info["cpu_model"] = [l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            info["cgroup_" + os.path.basename(path)] = open(path).read().strip()
+        except Exception:
+            pass
+    threads = info["affinity_cpus"]
+    try:   # cgroup v2 quota "max 100000" or "<quota> <period>"
+        q, per = info.get("cgroup_cpu.max", "max 100000").split()
+        if q != "max":
+            threads = max(1, min(threads, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    info["threads_used"] = threads
+    return info
+
+
+class CpuScan:
+    """The reference's ungapped_alignment on the host cores the way runFilterOnCpu runs it: one persistent thread team with one
+    SmithWaterman per thread (oracle/_ref: ref_scan_init / ref_scan_batch), or the C port when oracle/_ref is absent."""
+
+    def __init__(self, res, off, threads):
+        from oracle.pyoracle import Oracle, Ref
+        self.res, self.off64, self.threads = res, np.ascontiguousarray(off, np.int64), threads
+        self.kind = "reference" if Ref.available() else "port"
+        self.max_len = int((self.off64[1:] - self.off64[:-1]).max())
+        if self.kind == "reference":
+            self.ref = Ref()
+            self.team = self.ref.scan_team(max(self.max_len, 1024), True, threads)
         else:
-            cb, bias = orc.query_cb(q, True)
-            orc.ungapped(q, cb, bias, res, off64, nthreads=threads)
-        dt += time.perf_counter() - t0
-        cells += float(len(q)) * float(off64[-1])
-        nq += 1
-    return {"value": cells / 1e9 / dt, "unit": METRIC, "cores": threads, "kind": "reference" if use_ref else "port",
-            "sample": "%d queries x whole %d-sequence DB = %.3g cells in %.1f s" % (nq, len(off64) - 1, cells, dt)}
+            mat, pb = load_matrix()
+            self.orc = Oracle(mat, pb)
+
+    def scan(self, queries, n_targets=None):
+        """-> u8/int32 scores [nq][n]"""
+        toff = self.off64 if n_targets is None else self.off64[:n_targets + 1]
+        if self.kind == "reference":
+            return self.ref.scan_batch(self.team, queries, self.res, toff)
+        out = []
+        for q in queries:
+            cb, bias = self.orc.query_cb(q, True)
+            out.append(self.orc.ungapped(q, cb, bias, self.res, toff, nthreads=self.threads, fast=True))
+        return np.stack(out)
+
+    def close(self):
+        if self.kind == "reference":
+            self.ref.scan_free(self.team)
+
+
+def hit_list_from_scores(scores, thr, k):
+    """the filter/sort/truncate of runFilterOnCpu (ungappedprefilter.cpp:450-478): score > thr, (score desc, id asc), first k"""
+    ids = np.nonzero(scores > thr)[0]
+    order = np.lexsort((ids, -scores[ids].astype(np.int64)))[:k]
+    return ids[order].astype(np.uint32), scores[ids[order]].astype(np.int32)
+
+
+def cpu_reference_gcups(batch_queries, res, off, budget_s, gpu_dense=None, gpu_hits=None, thr=15, max_hits=300):
+    """cpu_baseline of the scan: the same query batches as the GPU arm, whole DB, all usable host threads, until the budget is spent;
+    plus a 1-thread figure on a bounded sample, and the at-scale parity check: the reference's scores of every target (and the hit
+    lists they imply) for the queries it got through, against what the GPU produced for the same queries."""
+    ci = cpu_info()
+    threads = ci["threads_used"]
+    off64 = np.ascontiguousarray(off, np.int64)
+    db_res = float(off64[-1])
+    one = CpuScan(res, off, 1)
+    n1 = int(min(len(off64) - 1, 40000))
+    one.scan(batch_queries[0][:1], 2000)
+    t0 = time.perf_counter()
+    one.scan(batch_queries[0][:1], n1)
+    gc1 = len(batch_queries[0][0]) * float(off64[n1]) / 1e9 / (time.perf_counter() - t0)
+    one.close()
+    cs = CpuScan(res, off, threads)
+    cs.scan(batch_queries[0][:1], min(len(off64) - 1, 20000))      # warm: page in, spin up the team
+    cells, dt, nq, same_scores, same_hits, checked = 0.0, 0.0, 0, True, True, 0
+    for bi, qs in enumerate(batch_queries):
+        pos = 0
+        while pos < len(qs) and dt < budget_s:
+            part = qs[pos:pos + 4]
+            t0 = time.perf_counter()
+            sc = cs.scan(part)
+            dt += time.perf_counter() - t0
+            cells += float(sum(len(q) for q in part)) * db_res
+            if gpu_dense is not None and bi < len(gpu_dense):
+                for k in range(len(part)):
+                    same_scores &= bool(np.array_equal(sc[k].astype(np.uint8), gpu_dense[bi][pos + k]))
+                    if gpu_hits is not None:
+                        ids, scs = hit_list_from_scores(sc[k].astype(np.int32), thr, max_hits)
+                        gi, gs = gpu_hits[bi][pos + k]
+                        same_hits &= bool(np.array_equal(ids, gi) and np.array_equal(scs, gs))
+                    checked += 1
+            pos += len(part)
+            nq += len(part)
+        if dt >= budget_s:
+            break
+    cs.close()
+    out = {"value": cells / 1e9 / dt, "unit": METRIC, "cores": threads, "kind": cs.kind, "gcups_1_thread": gc1, "host": ci,
+           "sample": "%d queries (the GPU arm's own batches, in order) x whole %d-sequence DB = %.3g cells in %.1f s; 1-thread figure on "
+                     "1 query x %d targets; persistent thread team, one SmithWaterman per thread" % (nq, len(off64) - 1, cells, dt, n1)}
+    if gpu_dense is not None:
+        out["scan_identical_to_gpu"] = bool(same_scores) and checked > 0
+        out["hit_lists_identical_to_gpu"] = bool(same_hits) and checked > 0
+        out["queries_compared_with_gpu"] = checked
+        out["scores_compared_with_gpu"] = checked * (len(off64) - 1)
+    return out
 
 
 def cpu_reference_align_step(queries, tdata, toff, lists, gpu_results, gpu_pool, budget_s, threads):
@@ -239,42 +323,47 @@ def cpu_reference_sw(queries, td, to, pairs, budget_s, threads):
 
 
 def run_reference_arm(args):
+    """--impl reference: the reference's own CPU scorer on the same workload and the same step shape as the GPU arm (one step = one
+    batch of queries_per_step queries against the whole DB; the two batches alternate), all usable host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    res, off, queries = make_scan_workload(0, args.db_seqs, 4, 2)
-    # a step = one query against the whole DB (the reference's own unit of work: one runFilterOnCpu pass)
-    from oracle.pyoracle import Ref, Oracle
-    mat, pb = load_matrix()
-    off64 = off.astype(np.int64)
-    use_ref = Ref.available()
-    ref = Ref() if use_ref else None
-    orc = None if use_ref else Oracle(mat, pb)
-    times, cells_done, m = [], 0.0, len(off64) - 1
+    ci = cpu_info()
+    threads = ci["threads_used"]
+    n_distinct = 2
+    res, off, queries = make_scan_workload(0, args.db_seqs, args.queries_per_step, n_distinct)
+    batches = [queries[b * args.queries_per_step:(b + 1) * args.queries_per_step] for b in range(n_distinct)]
+    db_res = float(np.asarray(off, np.int64)[-1])
+    cs = CpuScan(res, off, threads)
+    cs.scan(batches[0][:1], min(len(off) - 1, 20000))
+    times, cells_done = [], 0.0
     for s in range(args.warmup + args.steps):
-        q = queries[s % len(queries)]
+        qs = batches[s % n_distinct]
         t0 = time.perf_counter()
-        if use_ref:
-            ref.ungapped(q, True, res, off64, nthreads=threads)
-        else:
-            cb, bias = orc.query_cb(q, True)
-            orc.ungapped(q, cb, bias, res, off64, nthreads=threads)
+        cs.scan(qs)
         dt = time.perf_counter() - t0
-        cells = float(len(q)) * float(off64[-1])
         if s >= args.warmup:
-            times.append(dt); cells_done += cells
+            times.append(dt); cells_done += float(sum(len(q) for q in qs)) * db_res
+    cs.close()
     total = sum(times)
     val = cells_done / 1e9 / total
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, len(times)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "ungapped prefilter (BASELINE config[1]): L~350 queries vs %d-seq synthetic DB; CPU step = "
-                                   "1 query x the whole %d-sequence DB" % (args.db_seqs, m)},
-            "cpu_baseline": {"value": val, "unit": METRIC, "cores": threads, "kind": "reference" if use_ref else "port",
-                             "sample": "%d steps x %.3g cells" % (len(times), cells)},
+            "config": scan_config(args, int(db_res), 1),
+            "cpu_baseline": {"value": val, "unit": METRIC, "cores": threads, "kind": cs.kind, "host": ci,
+                             "sample": "%d steps x %d queries x whole DB (%.3g cells per step)" % (len(times), args.queries_per_step, cells_done / max(1, len(times)))},
             "e2e": {"value": val, "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def scan_config(args, db_residues, world):
+    return {"workload": "ungapped prefilter (BASELINE config[1]): L~350 protein queries vs %d-seq synthetic DB "
+                        "(log-normal lengths, %d residues), BLOSUM62 + composition bias; a step = %d queries x the whole DB "
+                        "(a sample of the 10k-query job: the rate does not depend on the number of steps)" % (args.db_seqs, db_residues, args.queries_per_step),
+            "queries_per_step_per_gpu": args.queries_per_step, "db_seqs": args.db_seqs, "max_hits": args.max_hits,
+            "parallelism": "query-sharded x%d, DB replicated" % world,
+            "l2": "target DB (%d MB) larger than L2; two alternating query batches" % (db_residues >> 20)}
 
 
 def main():
@@ -291,6 +380,7 @@ def main():
     ap.add_argument("--sw-targets", type=int, default=256)
     ap.add_argument("--nucl-reads", type=int, default=200000)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the scan's cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -388,6 +478,16 @@ def main():
     h2d = sum(p.profile.nbytes for p in batches[0])
     d2h = len(batches[0]) * (args.max_hits * 8 + 4)
 
+    # what the GPU produced for both batches (every target's score + the hit lists), kept for the at-scale parity check of the
+    # cpu_baseline leg; fetched now because the secondaries below load other DBs into the context
+    gpu_dense, gpu_hits = [], []
+    if rank == 0 and world == 1 and not args.no_cpu:
+        for j in jobs:
+            j.run()
+            h, nh, dn = j.fetch(want_dense=True)
+            gpu_dense.append(dn)
+            gpu_hits.append([(h[i]["id"][:int(nh[i])].copy(), h[i]["score"][:int(nh[i])].copy()) for i in range(len(h))])
+
     # ---- reduce over ranks (max time, sum cells) ---------------------------------------------------------
     if dist is not None:
         t = torch.tensor([step_ms, e2e_s, float(total_cells), float(e2e_cells)], dtype=torch.float64, device="cuda")
@@ -401,11 +501,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "s16x2", "data": "synthetic",
-            "config": {"workload": "ungapped prefilter (BASELINE config[1]): L~350 protein queries vs %d-seq synthetic DB "
-                                   "(log-normal lengths, %d residues), BLOSUM62 + composition bias" % (args.db_seqs, db_residues),
-                       "queries_per_step_per_gpu": args.queries_per_step, "db_seqs": args.db_seqs, "max_hits": args.max_hits,
-                       "parallelism": "query-sharded x%d, DB replicated" % world,
-                       "l2": "target DB (%d MB) larger than L2; two alternating query batches" % (db_residues >> 20)},
+            "config": scan_config(args, db_residues, world),
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clocks, "device": info}
 
@@ -542,7 +638,7 @@ def main():
                     sec["score_endpos"]["roofline"] = {"bound": "int-pipe", "achieved": ach, "peak": pk, "frac": ach / pk,
                                                        "ops_per_cell": SW32_OPS_PER_CELL}
                 if not args.no_cpu:
-                    sec["cpu_baseline"] = cpu_reference_sw(sq, std, sto, spairs, 10.0, os.cpu_count() or 1)
+                    sec["cpu_baseline"] = cpu_reference_sw(sq, std, sto, spairs, 10.0, cpu_info()["threads_used"])
                 # (c) the whole `align` step for these lists: b200_align_batch (score/end -> E-value + coverage gate -> start -> CIGAR ->
                 #     result assembly, criteria, ordering) and the records of Matcher::resultToBuffer, host buffers end to end
                 try:
@@ -561,7 +657,7 @@ def main():
                             "alignments_per_s": n_aln / a_dt, "ms": a_dt * 1e3, "alignments": n_aln,
                             "accepted": int(sum(len(r) for r in ares)), "unit": "alignments/s", "GCUPS_equivalent": sw_cells / 1e9 / a_dt}
                     if not args.no_cpu:
-                        step["cpu_baseline"] = cpu_reference_align_step(sq, std, sto, lists, ares, apool, 8.0, os.cpu_count() or 1)
+                        step["cpu_baseline"] = cpu_reference_align_step(sq, std, sto, lists, ares, apool, 8.0, cpu_info()["threads_used"])
                     sec["align_step"] = step
                 except Exception as e:  # pragma: no cover
                     sec["align_step"] = {"error": repr(e)}
@@ -597,10 +693,10 @@ def main():
                         ref = Ref()
                         m = min(len(reads), 200000)
                         t0 = time.perf_counter()
-                        rout = ref.nucl_align_batch(reads[:m], ntd, nto.astype(np.int64), ntasks[:m], nthreads=os.cpu_count() or 1)
+                        rout = ref.nucl_align_batch(reads[:m], ntd, nto.astype(np.int64), ntasks[:m], nthreads=cpu_info()["threads_used"])
                         rdt = time.perf_counter() - t0
                         same = bool(np.array_equal(rout[:, :5], np.stack([nout[f][:m] for f in ("score", "qstart", "qend", "dbstart", "dbend")], 1)))
-                        nsec["cpu_baseline"] = {"value": m / rdt, "unit": "alignments/s", "cores": os.cpu_count() or 1, "kind": "reference",
+                        nsec["cpu_baseline"] = {"value": m / rdt, "unit": "alignments/s", "cores": cpu_info()["threads_used"], "kind": "reference",
                                                 "sample": "%d reads in %.2f s" % (m, rdt), "results_identical_to_gpu": same}
                 line.setdefault("secondary", {})["nucl_align"] = nsec
             except Exception as e:  # pragma: no cover
@@ -609,7 +705,7 @@ def main():
         # ---- CPU baseline (bounded sample, rank 0, N=1 only) ---------------------------------------------------
         if not args.no_cpu and world == 1:
             try:
-                line["cpu_baseline"] = cpu_reference_gcups(queries, res, off, 12.0, os.cpu_count() or 1)
+                line["cpu_baseline"] = cpu_reference_gcups(batch_seqs, res, off, args.cpu_budget, gpu_dense, gpu_hits, 15, args.max_hits)
             except Exception as e:  # pragma: no cover
                 line["cpu_baseline"] = {"error": repr(e)}
         print(json.dumps(line))

@@ -75,11 +75,11 @@ class Oracle:
         bias = self.lib.orc_ssw_bias(_p(self.mat), self.A, _p(cb), len(q), 1 if comp_bias else 0)
         return cb, int(bias)
 
-    def ungapped(self, q, cb, bias, tdata, toff, nthreads=8):
+    def ungapped(self, q, cb, bias, tdata, toff, nthreads=8, fast=False):
         q = np.ascontiguousarray(q, np.uint8)
         n = len(toff) - 1
         out = np.zeros(n, np.int32)
-        self.lib.orc_ungapped_alignment_batch(_p(self.mat), self.A, _p(q), len(q), _p(cb), bias, _p(tdata), _p(toff),
+        (self.lib.orc_ungapped_alignment_batch_fast if fast else self.lib.orc_ungapped_alignment_batch)(_p(self.mat), self.A, _p(q), len(q), _p(cb), bias, _p(tdata), _p(toff),
                                               ctypes.c_int64(n), _p(out), nthreads)
         return out
 
@@ -341,6 +341,23 @@ class Ref:
         self.lib.ref_ungapped_alignment(_p(q), len(q), 1 if comp_bias else 0, _p(tdata), _p(toff), ctypes.c_int64(n),
                                         _p(out), nthreads)
         return out
+
+    def scan_team(self, max_len, comp_bias=True, nthreads=8):
+        """persistent thread team + per-thread SmithWaterman objects (ref_scan_init); use with scan_batch / scan_free"""
+        self.lib.ref_scan_init.restype = ctypes.c_void_p
+        return ctypes.c_void_p(self.lib.ref_scan_init(ctypes.c_int64(int(max_len)), 1 if comp_bias else 0, int(nthreads)))
+
+    def scan_batch(self, team, queries, tdata, toff, out=None):
+        """ungapped_alignment of every query against every target on the team; -> u8 [nq][n]"""
+        qd, qo = pack_targets([np.ascontiguousarray(q, np.uint8) for q in queries])
+        n = len(toff) - 1
+        if out is None:
+            out = np.empty((len(queries), n), np.uint8)
+        self.lib.ref_scan_batch(team, _p(qd), _p(qo), ctypes.c_int64(len(queries)), _p(tdata), _p(toff), ctypes.c_int64(n), _p(out))
+        return out
+
+    def scan_free(self, team):
+        self.lib.ref_scan_free(team)
 
     def sw_score_endpos(self, q, comp_bias, tdata, toff, go=11, ge=1, nthreads=8):
         q = np.ascontiguousarray(q, np.uint8)

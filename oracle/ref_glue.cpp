@@ -186,6 +186,54 @@ void ref_ungapped_alignment(const unsigned char *q, int qL, int compBias, const 
     }
 }
 
+// A2 as the prefilter runs it (runFilterOnCpu, ungappedprefilter.cpp:359-481): ONE persistent thread team with one SmithWaterman per
+// thread for the whole run; per query every thread runs ssw_init on its own object, then the targets are split over the team.
+// init / scan / free so that bench.py times steps (batches of queries) without rebuilding the team or the per-thread objects.
+struct ScanTeam {
+    int nthreads;
+    bool biasCorr;
+    std::vector<PerThread> p;
+};
+
+void *ref_scan_init(int64_t maxLen, int compBias, int nthreads) {
+    ScanTeam *t = new ScanTeam();
+    t->nthreads = nthreads;
+    t->biasCorr = compBias != 0;
+    t->p.resize(nthreads);
+#pragma omp parallel num_threads(nthreads)
+    {
+        ensure(t->p[omp_get_thread_num()], (size_t) maxLen, compBias != 0);
+    }
+    return t;
+}
+
+// nQ queries (concatenated residues + offsets) against n targets; out[qi*n + i] = u8 score (the reference's scores never exceed 255).
+void ref_scan_batch(void *handle, const unsigned char *qdata, const int64_t *qoff, int64_t nQ, const unsigned char *tdata,
+                    const int64_t *toff, int64_t n, uint8_t *out) {
+    ScanTeam *t = (ScanTeam *) handle;
+#pragma omp parallel num_threads(t->nthreads)
+    {
+        PerThread &p = t->p[omp_get_thread_num()];
+        for (int64_t qi = 0; qi < nQ; qi++) {
+            const int qL = (int) (qoff[qi + 1] - qoff[qi]);
+            mapNumeric(p.q, g_aa, qdata + qoff[qi], qL);
+            p.sw->ssw_init(p.q, g_tiny, g_aa);
+            uint8_t *o = out + (size_t) qi * n;
+#pragma omp for schedule(dynamic, 256) nowait
+            for (int64_t i = 0; i < n; i++) {
+                o[i] = (uint8_t) p.sw->ungapped_alignment(tdata + toff[i], (int32_t) (toff[i + 1] - toff[i]));
+            }
+        }
+    }
+}
+
+void ref_scan_free(void *handle) {
+    ScanTeam *t = (ScanTeam *) handle;
+    if (t == NULL) return;
+    for (size_t i = 0; i < t->p.size(); i++) { delete t->p[i].sw; delete t->p[i].q; delete t->p[i].t; }
+    delete t;
+}
+
 // A3/A4: alignScoreEndPos<SEQ_SEQ>; out[i*4+{0,1,2,3}] = score1, qEndPos1, dbEndPos1, word
 void ref_sw_score_endpos(const unsigned char *q, int qL, int compBias, const unsigned char *tdata,
                          const int64_t *toff, int64_t n, int gapOpen, int gapExtend, int32_t *out, int nthreads) {

@@ -376,3 +376,30 @@ def test_error_paths(ctx, submat, blosum):
     ctx.load_db(res, off, 21)
     out = ctx.sw_score_endpos([q], np.zeros((0, 2), np.uint32))     # empty batch is fine
     assert len(out) == 0
+
+
+def test_scan_at_scale_vs_oracle(ctx, oracle, submat, blosum):
+    """the scan where it is benchmarked: a 200 000-sequence DB (every target-length regime, persistent CTAs with dynamic units,
+    several capacity classes in one call) against the multi-threaded C restatement -- every score and the hit lists."""
+    import os
+    rng = np.random.default_rng(20260923)
+    bg = synth.background(blosum[1])
+    res, off = synth.random_seqs(rng, 200000, bg, mean=300, sigma=0.6, lo=30, hi=5000)
+    qs = [synth.random_seqs(rng, 1, bg, mean=L, sigma=0, lo=L, hi=L, normal=True)[0] for L in (207, 351, 352, 489)]
+    synth.plant_homologs(rng, res, off, qs, bg, frac=0.01)
+    synth.plant_homologs(rng, res, off, qs, bg, frac=0.002, subst=0.05)     # near-identical copies: saturating scores
+    profs = [submat.ssw_query(q) for q in qs]
+    ctx.load_db(res, off, 21)
+    hits, n_hits, dense = ctx.ungapped_scan(profs, min_score_excl=15, max_hits=300, want_dense=True)
+    off64 = off.astype(np.int64)
+    nthreads = len(os.sched_getaffinity(0))
+    saturated = 0
+    for i, q in enumerate(qs):
+        cb, bias = oracle.query_cb(q, True)
+        exp = oracle.ungapped(q, cb, bias, res, off64, nthreads=nthreads, fast=True)
+        assert np.array_equal(dense[i].astype(np.int32), exp), (i, np.nonzero(dense[i] != exp)[0][:5])
+        eid, esc = _expected_hits(exp, 15, 300)
+        assert n_hits[i] == len(eid)
+        assert np.array_equal(hits[i]["id"][:len(eid)], eid) and np.array_equal(hits[i]["score"][:len(eid)], esc)
+        saturated += int((exp == 255 - bias).sum())
+    assert saturated > 0

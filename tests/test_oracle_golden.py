@@ -74,3 +74,26 @@ def test_backtrace_and_identities(golden, oracle):
             assert bt == str(bts[k]) and ids == ident[k], (i, k)
             n_gapped += ("I" in bt) or ("D" in bt)
     assert n_gapped > 100
+
+
+def test_fast_scan_restatement_equals_literal(oracle):
+    """orc_ungapped_alignment_batch_fast (row-vectorised, used for the at-scale GPU parity test and the "port" CPU baseline) gives the
+    scores of the literal restatement orc_ungapped_alignment on random + planted-homolog targets, incl. saturating ones."""
+    import os
+    from mmseqs2_b200 import synth
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "blosum62.npz"))
+    rng = np.random.default_rng(11)
+    bg = synth.background(d["pback"])
+    res, off = synth.random_seqs(rng, 1500, bg, mean=250, sigma=0.7, lo=1, hi=2500)
+    qs = synth.split(*synth.random_seqs(rng, 4, bg, mean=300, sigma=120, lo=1, hi=700, normal=True))
+    synth.plant_homologs(rng, res, off, qs, bg, frac=0.1, subst=0.05)
+    off64 = off.astype(np.int64)
+    saturated = 0
+    for q in qs:
+        for cbf in (True, False):
+            cb, bias = oracle.query_cb(q, cbf)
+            a = oracle.ungapped(q, cb, bias, res, off64)
+            b = oracle.ungapped(q, cb, bias, res, off64, fast=True)
+            assert np.array_equal(a, b)
+            saturated += int((a == 255 - bias).sum())
+    assert saturated > 0
