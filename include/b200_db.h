@@ -59,7 +59,9 @@ int b200_align_db(b200_ctx *ctx, const char *query_db, const char *target_db, co
 /* `mmseqs ungappedprefilter` on DB files (amino-acid sequence queries, PREF_MODE_UNGAPPED: runFilterOnCpu / runFilterOnGpu,
  * src/prefiltering/ungappedprefilter.cpp:346-482, :41-343): every query against every target with the saturating ungapped scorer,
  * hits with score > min_diag_score, ordered by (score desc, target key asc), truncated to max_res_list_len, written as prefilter
- * records "key \t score \t 0".  Identity inclusion (same query/target DB) is not applied.  n_hits may be NULL. */
+ * records "key \t score \t 0".  Soft-masked (lowercase) target residues score as X, as in runFilterOnCpu (:401-404).  Not applied:
+ * identity inclusion (same query/target DB keeps its self hit only through its score) and the canBeCovered pre-check (:409-411), which is
+ * a no-op at the default -c 0.  n_hits may be NULL. */
 int b200_prefilter_db(b200_ctx *ctx, const char *query_db, const char *target_db, const char *prefilter_db, const int16_t *sub_matrix,
                       const double *p_back, const char *num2aa, int alphabet, int comp_bias, float comp_bias_scale, int min_diag_score,
                       uint32_t max_res_list_len, uint32_t bucket_queries, uint64_t *n_hits);

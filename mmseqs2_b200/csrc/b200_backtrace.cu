@@ -73,6 +73,7 @@ sw_backtrace_kernel(const BtTask *__restrict__ tasks, unsigned n_tasks, const in
         int8_t *dl = direction;
         long long width = 0, width_d = 0, zeroed = 0;
         int maxv = 0;
+        bool covered = false;
         int32_t *hb = srows[warp][0], *eb = srows[warp][1], *hc = srows[warp][2];
         bool in_smem = true;
         do {
@@ -159,18 +160,23 @@ sw_backtrace_kernel(const BtTask *__restrict__ tasks, unsigned n_tasks, const in
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) { const int v = __shfl_xor_sync(0xffffffffu, lmax, o); lmax = lmax > v ? lmax : v; }
             maxv = maxv > lmax ? maxv : lmax;
+            // a band that already spans the whole rectangle cannot find more: stop there even if the claimed score was not reached
+            // (inconsistent caller input, or a score capped at 32767) -- the rows and the direction buffer are sized for exactly this
+            // bound (final band < 2 * max_span); the reference would keep doubling and reallocating (StripedSmithWaterman.cpp:1614-1640)
+            covered = band >= (q_len > db_len ? q_len : db_len);
             band *= 2;
-        } while (maxv < tk.score && band <= (1 << 28));
+        } while (maxv < tk.score && !covered && band <= (1 << 28));
         band /= 2;
+        const bool reached = maxv >= tk.score;
         if (PASS == 1) { if (lane == 0) out_band[ti] = band; continue; }
         __syncwarp();                                    // the direction bytes of every lane are visible to lane 0
         if (lane != 0) continue;                         // lane 0 walks back; the other lanes wait at the next task fetch
         // ---- trace back (bottom-right corner to the origin), ops emitted end -> start, then reversed
         uint32_t *c = cigars + cigar_off[ti];
         int i = q_len - 1, j = db_len - 1, e = 0, n = 0, state = 2;
-        bool ok = true;
+        bool ok = reached;      // score not reachable inside the rectangle: no CIGAR, ok = 0
         char op = 'M', prev_op = 'M';
-        while (i > 0 || j > 0) {
+        while (ok && (i > 0 || j > 0)) {
             const long long idx = band_d(band, i, j, state);
             switch (dl[idx]) {
                 case 1: --i; --j; state = 2; dl -= width_d * 3; op = 'M'; break;

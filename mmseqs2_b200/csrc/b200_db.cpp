@@ -71,25 +71,39 @@ int b200h_db_open(const char *data_path, b200h_db **out) {
     if (!read_file(base + ".index", idx)) { delete db; return db_fail("cannot open index file " + base + ".index"); }
     idx.push_back('\0');
     const char *p = idx.data();
+    const uint64_t data_size = db->data.size() - 1;   // without the sentinel NUL appended above
     while (*p != '\0') {
-        // key \t offset \t length \n   (DBReader::readIndex)
-        char *end = nullptr;
+        // key \t offset \t length \n   (DBReader::readIndex) -- all three fields on this line, nothing borrowed from the next one
+        const char *eol = p;
+        while (*eol != '\n' && *eol != '\0') eol++;
+        uint64_t f[3];
+        const char *c = p;
+        bool ok = true;
+        for (int k = 0; k < 3 && ok; k++) {
+            while (c < eol && (*c == ' ' || *c == '\t')) c++;
+            if (c >= eol || *c < '0' || *c > '9') { ok = false; break; }
+            uint64_t v = 0;
+            while (c < eol && *c >= '0' && *c <= '9') { v = v * 10 + (uint64_t) (*c - '0'); c++; }
+            f[k] = v;
+        }
+        if (!ok) { delete db; return db_fail("malformed index line in " + base + ".index"); }
         IndexEntry e;
-        e.key = (uint32_t) strtoull(p, &end, 10);
-        if (end == p) { delete db; return db_fail("malformed index line in " + base + ".index"); }
-        p = end; e.offset = strtoull(p, &end, 10);
-        if (end == p) { delete db; return db_fail("malformed index line in " + base + ".index"); }
-        p = end; e.length = strtoull(p, &end, 10);
-        if (end == p) { delete db; return db_fail("malformed index line in " + base + ".index"); }
-        p = end;
-        while (*p != '\n' && *p != '\0') p++;
-        if (*p == '\n') p++;
-        if (e.offset + e.length > db->data.size()) { delete db; return db_fail("index entry beyond the data file in " + base); }
+        e.key = (uint32_t) f[0]; e.offset = f[1]; e.length = f[2];
+        // every entry carries at least its NUL (DBWriter::writeEnd); offset + length must not wrap
+        if (e.length == 0 || e.length > data_size || e.offset > data_size - e.length) { delete db; return db_fail("index entry beyond the data file (or empty) in " + base); }
         db->index.push_back(e);
+        p = (*eol == '\n') ? eol + 1 : eol;
     }
     std::stable_sort(db->index.begin(), db->index.end(), [](const IndexEntry &a, const IndexEntry &b) { return a.key < b.key; });
     std::vector<char> ty;
-    if (read_file(base + ".dbtype", ty) && ty.size() >= 4) { int32_t v; memcpy(&v, ty.data(), 4); db->dbtype = v; }
+    if (read_file(base + ".dbtype", ty) && ty.size() >= 4) {
+        int32_t v; memcpy(&v, ty.data(), 4);
+        // bit 31 = zstd-compressed entries (DBReader::isCompressed), extended flag 8 = GPU-padded residues (Parameters.h:94): such DBs
+        // need zstd / un-padding, which this reader does not do -- refuse instead of misreading them as text
+        const uint32_t ext = ((uint32_t) v >> 16) & 0x7FFEu;                       // DBReader::getExtendedDbtype
+        if (((uint32_t) v & (1u << 31)) != 0 || (ext & 8u) != 0) { delete db; return db_fail("compressed or GPU-padded DB: not supported by b200h_db_open: " + base); }
+        db->dbtype = v;
+    }
     *out = db;
     return B200_OK;
 }
@@ -298,7 +312,9 @@ int b200_align_db(b200_ctx *ctx, const char *query_db, const char *target_db, co
 
 namespace {
 // numeric residues of every entry of a sequence DB (Sequence::mapSequence: length = index length - 2)
-void load_sequences(const b200h_db *db, const uint8_t a2n[256], std::vector<uint8_t> &res, std::vector<uint64_t> &off, std::vector<uint32_t> &keys) {
+// lower_to_x: soft-masked (lowercase) residues become X, as runFilterOnCpu does with the targets before scoring (ungappedprefilter.cpp:401-404)
+void load_sequences(const b200h_db *db, const uint8_t a2n[256], std::vector<uint8_t> &res, std::vector<uint64_t> &off, std::vector<uint32_t> &keys,
+                    bool lower_to_x = false) {
     const uint64_t n = b200h_db_size(db);
     off.assign(n + 1, 0);
     for (uint64_t i = 0; i < n; i++) {
@@ -310,7 +326,8 @@ void load_sequences(const b200h_db *db, const uint8_t a2n[256], std::vector<uint
     for (uint64_t i = 0; i < n; i++) {
         const char *s = b200h_db_data(db, i);
         uint8_t *d = res.data() + off[i];
-        for (uint64_t j = 0; j < off[i + 1] - off[i]; j++) d[j] = a2n[(unsigned char) s[j]];
+        const uint8_t x = a2n[(unsigned char) 'X'];
+        for (uint64_t j = 0; j < off[i + 1] - off[i]; j++) d[j] = (lower_to_x && (unsigned char) s[j] >= 97) ? x : a2n[(unsigned char) s[j]];
         keys[i] = b200h_db_key(db, i);
     }
 }
@@ -337,7 +354,7 @@ int b200_prefilter_db(b200_ctx *ctx, const char *query_db, const char *target_db
         std::vector<uint8_t> tres, qres;
         std::vector<uint64_t> toff, qoff;
         std::vector<uint32_t> tkeys, qkeys;
-        load_sequences(tdb, a2n, tres, toff, tkeys);
+        load_sequences(tdb, a2n, tres, toff, tkeys, /*lower_to_x=*/true);
         load_sequences(qdb, a2n, qres, qoff, qkeys);
         rc = b200_db_load(ctx, tres.data(), toff.data(), tkeys.size(), alphabet);
         const uint64_t nq = qkeys.size();

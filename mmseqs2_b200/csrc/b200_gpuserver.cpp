@@ -100,18 +100,12 @@ int b200_gpuserver_serve(b200_server *s, uint64_t max_requests) {
         int rc = B200_OK;
         if (L <= 0 || (unsigned) L > h->maxSeqLen) rc = B200_ERR_ARG;
         if (rc == B200_OK) {
-            // composition bias of every position = profile - matrix column; the SSW bias constant follows (b200_host.h)
-            cb.assign((size_t) L, 0);
-            bool any = false;
-            for (int j = 0; j < L && rc == B200_OK; j++) {
+            // SSW bias from the request itself: matrix column + one composition bias per position for sequence queries, the profile
+            // rule otherwise (the reference client also sends profile_for_alignment of HMM queries) -- b200h_ssw_bias_from_profile
+            for (int j = 0; j < L; j++)
                 if (q[j] >= s->A) { rc = B200_ERR_ARG; break; }
-                const int d = (int) prof[j] - (int) s->mat[q[j]];           // residue row 0: profile[0][j] = mat[0][q[j]] + cb[j]
-                if (d < -128 || d > 127) { rc = B200_ERR_ARG; break; }
-                cb[j] = (int8_t) d;
-                any |= d != 0;
-            }
             if (rc == B200_OK) {
-                b200_query bq; bq.profile = prof; bq.qlen = L; bq.bias = b200h_ssw_bias(s->mat.data(), s->A, cb.data(), L, any ? 1 : 0);
+                b200_query bq; bq.profile = prof; bq.qlen = L; bq.bias = b200h_ssw_bias_from_profile(s->mat.data(), s->A, q, L, prof);
                 rc = b200_ungapped_scan(s->ctx, &bq, 1, s->min_score, h->maxResListLen, hits.data(), &n, nullptr);
             }
         }

@@ -28,7 +28,11 @@ struct DevPool {
     std::mutex mu;
     std::vector<Slot> free_list;
     size_t held = 0;
+    bool dirty = false;   // a buffer was returned since the last device-wide synchronisation
     static DevPool &get() { static DevPool pool; return pool; }
+    // Buffers come back without a stream synchronisation (cudaFree would have synchronised implicitly), so work queued on the
+    // releasing context's stream may still be reading them.  Before the first buffer is handed out again after any release, the
+    // device is synchronised once: a few microseconds on an idle device, and it makes reuse across contexts / streams safe.
     void *take(size_t n, int dev, size_t *cap_out) {
         std::lock_guard<std::mutex> lk(mu);
         int best = -1;
@@ -36,6 +40,7 @@ struct DevPool {
             if (free_list[i].dev == dev && free_list[i].cap >= n && free_list[i].cap <= 4 * n + (1u << 20) &&
                 (best < 0 || free_list[i].cap < free_list[best].cap)) best = (int) i;
         if (best < 0) return nullptr;
+        if (dirty) { cudaDeviceSynchronize(); dirty = false; }
         void *p = free_list[best].p;
         *cap_out = free_list[best].cap;
         held -= free_list[best].cap;
@@ -46,6 +51,7 @@ struct DevPool {
         std::lock_guard<std::mutex> lk(mu);
         if (free_list.size() >= 256 || held + cap > ((size_t) 32 << 30)) { cudaFree(p); return; }   // of 180 GB HBM
         Slot s = {p, cap, dev};
+        dirty = true;
         free_list.push_back(s);
         held += cap;
     }

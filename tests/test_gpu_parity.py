@@ -403,3 +403,22 @@ def test_scan_at_scale_vs_oracle(ctx, oracle, submat, blosum):
         assert np.array_equal(hits[i]["id"][:len(eid)], eid) and np.array_equal(hits[i]["score"][:len(eid)], esc)
         saturated += int((exp == 255 - bias).sum())
     assert saturated > 0
+
+
+def test_backtrace_unreachable_score_terminates(ctx, golden, golden_db, submat):
+    """a claimed score that no path inside the rectangle reaches (caller error, or a score capped at 32767): the band search stops
+    once the band covers the rectangle and the task comes back with ok == 0 -- it must neither run away nor write out of bounds"""
+    qs = _queries(golden)
+    n = len(golden["toff"]) - 1
+    pairs = np.array([(0, t) for t in range(n)], np.uint32)
+    profs = [submat.ssw_query(q) for q in qs[:1]]
+    aln = ctx.sw_align(profs, pairs)
+    good = np.nonzero(aln["dbend"] != -1)[0]
+    assert len(good) > 10
+    bad = aln.copy()
+    bad["score"][good[::2]] += 500
+    out, bts = ctx.sw_backtrace(profs, qs[:1], pairs, bad)
+    assert (out["ok"][good[::2]] == 0).all() and (out["n_cigar"][good[::2]] == 0).all()
+    ref_out, ref_bts = ctx.sw_backtrace(profs, qs[:1], pairs, aln)
+    for k in good[1::2]:
+        assert out["ok"][k] == 1 and bts[k] == ref_bts[k]
