@@ -102,6 +102,29 @@ int b200_ungapped_scan(b200_ctx *ctx, const b200_query *queries, int n_queries, 
 int b200_diag_score(b200_ctx *ctx, const b200_query *q, const uint32_t *ids, const uint16_t *diagonals, uint64_t n,
                     uint8_t *counts, int32_t *raw);
 
+/* The same for many queries at once: queries[i] (each with its own diagonal-scorer profile) owns hits
+ * [hit_offsets[i], hit_offsets[i+1]) of ids / diagonals / counts / raw.  One upload, one launch, one download: the shape in which
+ * the k-mer prefilter's per-thread UngappedAlignment objects (QueryMatcher.cpp:73,131) can share a GPU without a round trip and a
+ * stream synchronisation per query. */
+int b200_diag_score_batch(b200_ctx *ctx, const b200_query *queries, int n_queries, const uint64_t *hit_offsets, const uint32_t *ids,
+                          const uint16_t *diagonals, uint8_t *counts, int32_t *raw);
+
+/* ---- rescorediagonal: DistanceCalculator::computeUngappedAlignment on ASCII sequences -------- */
+/* A resident ASCII copy of a sequence DB (entries as DBReader::getData returns them, without the trailing newline): sequence i =
+ * data[offsets[i] .. offsets[i+1]).  Independent of the numeric DB of b200_db_load: both can be resident. */
+int b200_db_load_ascii(b200_ctx *ctx, const char *data, const uint64_t *offsets, uint64_t n_seq);
+/* DistanceCalculator::LocalAlignment (src/alignment/DistanceCalculator.h:75-91) + the identical-residue count rescorediagonal.cpp:296-301
+ * derives from it (case-insensitive; modes 2-4 only, 0 otherwise) */
+typedef struct { int32_t score, start_pos, end_pos, diagonal_len, dist_to_diagonal, diagonal, identical; } b200_rescore;
+/* For every hit (ids[i], diagonals[i]) of every query: computeUngappedAlignment(query, qLen, target, tLen, diagonal, matrix, mode)
+ * (src/alignment/DistanceCalculator.h:93-174) as rescorediagonal.cpp:231-236 calls it.  queries: ASCII, concatenated, query i =
+ * query_data[query_offsets[i] .. query_offsets[i+1]) owning hits [hit_offsets[i], hit_offsets[i+1]).  ascii_matrix: [123][123] int8,
+ * SubstitutionMatrix::createAsciiSubMat (FastMatrix).  mode: Parameters::RESCORE_MODE_* 0 HAMMING, 1 SUBSTITUTION, 2 ALIGNMENT,
+ * 3 END_TO_END_ALIGNMENT, 4 WINDOW_QUALITY_ALIGNMENT.  The unsigned short diagonal aliases every real diagonal congruent to it
+ * mod 65536 (:98-112), handled as the reference does. */
+int b200_rescore_diagonal(b200_ctx *ctx, const char *query_data, const uint64_t *query_offsets, int n_queries, const uint64_t *hit_offsets,
+                          const uint32_t *ids, const uint16_t *diagonals, const int8_t *ascii_matrix, int mode, b200_rescore *out);
+
 /* ---- A3-A5: affine-gap local alignment --------------------------------------------------------- */
 /* score only (s_align.score1 as alignScoreEndPos reports it: exact, capped at 32767).  This is the fast path
  * (two targets per warp in int16x2); Matcher-level callers run it on every prefilter hit, apply the reference's

@@ -73,15 +73,7 @@ public:
     // them.  Masked residues are mapped to X (alphabetSize-1) as runFilterOnCpu does (ungappedprefilter.cpp:402-405).
     void *loadDb(char *data, size_t *offset, int32_t *length, size_t dbByteSize) {
         (void) dbByteSize;
-        std::vector<uint8_t> res;
-        std::vector<uint64_t> off(dbEntries_ + 1, 0);
-        for (size_t i = 0; i < dbEntries_; i++) {
-            off[i] = res.size();
-            const unsigned char *s = reinterpret_cast<const unsigned char *>(data) + offset[i];
-            for (int32_t j = 0; j < length[i]; j++) res.push_back(s[j] >= 32 ? (uint8_t) (alphabetSize_ - 1) : (uint8_t) s[j]);
-        }
-        off[dbEntries_] = res.size();
-        lastStatus_ = b200_db_load(dev_->ctx(), res.data(), off.data(), dbEntries_, alphabetSize_);
+        lastStatus_ = b200_db_load_padded(dev_->ctx(), reinterpret_cast<const uint8_t *>(data), offset, length, dbEntries_, alphabetSize_);
         return dev_;
     }
     void setDb(void *) {}
@@ -99,10 +91,32 @@ public:
         uint32_t n = 0;
         lastStatus_ = b200_ungapped_scan(dev_->ctx(), &q, 1, minScoreExcl_, (uint32_t) maxSeqs_, hits_.data(), &n, NULL);
         if (lastStatus_ != B200_OK) return st;
-        for (uint32_t i = 0; i < n; i++) results[i] = Result(hits_[i].id, hits_[i].score, 0, 0);
+        if (type_ == GAPLESS) {
+            for (uint32_t i = 0; i < n; i++) results[i] = Result(hits_[i].id, hits_[i].score, -1, -1);
+        } else {
+            // GAPLESS_SMITH_WATERMAN (what `search --gpu 1 --alignment-mode 1` selects, ungappedprefilter.cpp:151-152; libmarv:
+            // cudasw4.cuh:1003-1026): the best maxSeqs targets of the ungapped scan are rescored with the gapped kernel; results carry the
+            // gapped score and its end positions, ordered (gapped score desc, id asc).  ungappedprefilter.cpp:282-325 turns them
+            // into alignment records directly.
+            std::vector<b200_pair> pairs(n);
+            std::vector<b200_sw_end> ends(n);
+            for (uint32_t i = 0; i < n; i++) { pairs[i].query = 0; pairs[i].target = hits_[i].id; }
+            if (n > 0) {
+                lastStatus_ = b200_sw_score_endpos(dev_->ctx(), &q, 1, pairs.data(), n, gapOpen_, gapExtend_, ends.data());
+                if (lastStatus_ != B200_OK) return st;
+            }
+            std::vector<uint32_t> order(n);
+            for (uint32_t i = 0; i < n; i++) order[i] = i;
+            const b200_sw_end *e = ends.data();
+            const b200_hit *h = hits_.data();
+            std::sort(order.begin(), order.end(), [e, h](uint32_t a, uint32_t b) {
+                return e[a].score != e[b].score ? e[a].score > e[b].score : h[a].id < h[b].id; });
+            for (uint32_t i = 0; i < n; i++) results[i] = Result(hits_[order[i]].id, ends[order[i]].score, ends[order[i]].qend, ends[order[i]].dbend);
+        }
         st.results = n;
         return st;
     }
+    void setGapCosts(int open, int extend) { gapOpen_ = open; gapExtend_ = extend; }
 
 private:
     Device *dev_;
@@ -111,6 +125,7 @@ private:
     size_t maxSeqs_;
     AlignmentType type_;
     int minScoreExcl_;
+    int gapOpen_ = 11, gapExtend_ = 1;
     int lastStatus_ = B200_OK;
     std::vector<b200_hit> hits_;
 };

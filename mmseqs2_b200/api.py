@@ -64,6 +64,8 @@ class _CQuery(ctypes.Structure):
 HIT_DTYPE = np.dtype([("id", np.uint32), ("score", np.int32)])
 PAIR_DTYPE = np.dtype([("query", np.uint32), ("target", np.uint32)])
 END_DTYPE = np.dtype([("score", np.int32), ("qend", np.int32), ("dbend", np.int32), ("word", np.int32)])
+RESCORE_DTYPE = np.dtype([("score", np.int32), ("start_pos", np.int32), ("end_pos", np.int32), ("diagonal_len", np.int32),
+                          ("dist_to_diagonal", np.int32), ("diagonal", np.int32), ("identical", np.int32)])
 NUCL_TASK_DTYPE = np.dtype([("query", np.uint32), ("target", np.uint32), ("diagonal", np.uint16), ("reserved", np.uint16)])
 NUCL_ALN_DTYPE = np.dtype([("score", np.int32), ("qstart", np.int32), ("qend", np.int32), ("dbstart", np.int32), ("dbend", np.int32),
                            ("identical", np.int32), ("n_cigar", np.int32)])
@@ -276,6 +278,40 @@ class Context:
         cq = _cqueries([query])
         self._check(self.lib.b200_diag_score(self.h, cq, _p(ids), _p(dg), _u64(len(ids)), _p(cnt), _p(raw)))
         return cnt, raw
+
+    def diag_score_batch(self, queries, hit_lists, want_raw=False):
+        """queries[i] with hit_lists[i] = (ids, diagonals): one call, one launch (b200_diag_score_batch) -> [(counts, raw)]"""
+        off = np.zeros(len(queries) + 1, np.uint64)
+        off[1:] = np.cumsum([len(h[0]) for h in hit_lists])
+        ids = np.ascontiguousarray(np.concatenate([np.asarray(h[0], np.uint32) for h in hit_lists]), np.uint32)
+        dg = np.ascontiguousarray(np.concatenate([np.asarray(h[1], np.uint16) for h in hit_lists]), np.uint16)
+        cnt = np.zeros(len(ids), np.uint8)
+        raw = np.zeros(len(ids), np.int32) if want_raw else None
+        cq = _cqueries(queries)
+        self._check(self.lib.b200_diag_score_batch(self.h, cq, len(queries), _p(off), _p(ids), _p(dg), _p(cnt), _p(raw)))
+        o = off.astype(np.int64)
+        return [(cnt[o[i]:o[i + 1]], raw[o[i]:o[i + 1]] if want_raw else None) for i in range(len(queries))]
+
+    # ---- rescorediagonal (SURVEY 8f row 3)
+    def load_db_ascii(self, data, offsets):
+        data = np.ascontiguousarray(np.frombuffer(data, np.uint8) if isinstance(data, (bytes, bytearray)) else data, np.uint8)
+        off = np.ascontiguousarray(offsets, np.uint64)
+        self._check(self.lib.b200_db_load_ascii(self.h, _p(data), _p(off), _u64(len(off) - 1)))
+
+    def rescore_diagonal(self, queries_ascii, hit_lists, asciimat, mode):
+        """queries_ascii[i] (bytes) with hit_lists[i] = (ids, diagonals u16) -> structured array per hit (b200_rescore)"""
+        qd = np.frombuffer(b"".join(queries_ascii), np.uint8)
+        qo = np.zeros(len(queries_ascii) + 1, np.uint64)
+        qo[1:] = np.cumsum([len(q) for q in queries_ascii])
+        ho = np.zeros(len(queries_ascii) + 1, np.uint64)
+        ho[1:] = np.cumsum([len(h[0]) for h in hit_lists])
+        ids = np.ascontiguousarray(np.concatenate([np.asarray(h[0], np.uint32) for h in hit_lists]), np.uint32)
+        dg = np.ascontiguousarray(np.concatenate([np.asarray(h[1], np.uint16) for h in hit_lists]), np.uint16)
+        out = np.zeros(len(ids), RESCORE_DTYPE)
+        m = np.ascontiguousarray(asciimat, np.int8)
+        self._check(self.lib.b200_rescore_diagonal(self.h, _p(np.ascontiguousarray(qd)), _p(qo), len(queries_ascii), _p(ho), _p(ids), _p(dg),
+                                                   _p(m), int(mode), _p(out)))
+        return out
 
     # ---- A3-A5
     @staticmethod

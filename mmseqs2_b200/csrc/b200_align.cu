@@ -347,8 +347,10 @@ __device__ __forceinline__ Seg seg_combine(const Seg &L, const Seg &R) {
     return o;
 }
 
+struct DiagQuery { uint64_t prof_off; uint64_t hit_begin; int32_t qlen; int32_t pad_; };   // one query of a batched call
+
 __global__ void __launch_bounds__(256)
-diag_score_kernel(const int8_t *__restrict__ prof, int qlen, const uint8_t *__restrict__ db,
+diag_score_kernel(const int8_t *__restrict__ prof_base, const DiagQuery *__restrict__ dq, int nq, const uint8_t *__restrict__ db,
                   const uint64_t *__restrict__ off, const int32_t *__restrict__ len, const uint32_t *__restrict__ ids,
                   const uint16_t *__restrict__ diags, uint64_t n, uint8_t *__restrict__ counts,
                   int32_t *__restrict__ raw) {
@@ -357,6 +359,11 @@ diag_score_kernel(const int8_t *__restrict__ prof, int qlen, const uint8_t *__re
     for (uint64_t h = (uint64_t) blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); h < n; h += warps_total) {
         const bool skip_count = counts[h] != 0;
         if (skip_count && raw == nullptr) continue;
+        // the query this hit belongs to: last descriptor whose hit_begin <= h (hit lists are concatenated in query order)
+        int lo = 0, hi = nq - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (dq[mid].hit_begin <= h) lo = mid; else hi = mid - 1; }
+        const int8_t *prof = prof_base + dq[lo].prof_off;
+        const int qlen = dq[lo].qlen;
         const uint32_t id = ids[h];
         const uint16_t dg = diags[h];
         const int d = (int) (int16_t) dg;
@@ -1119,6 +1126,7 @@ void b200_destroy(b200_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     db_free(ctx);
+    b200_ascii_db_free(ctx);
     DevBuf *bufs[] = {&ctx->raw, &ctx->pad, &ctx->qdesc, &ctx->dense, &ctx->hits, &ctx->nhits, &ctx->pairs, &ctx->items,
                       &ctx->out4, &ctx->bnd, &ctx->ids, &ctx->diags, &ctx->counts, &ctx->rawout, &ctx->counter};
     for (DevBuf *b : bufs) b->release();
@@ -1171,8 +1179,8 @@ int b200_sync(b200_ctx *ctx) {
 // (the +32 soft-mask bit of the padded GPU DB, makepaddedseqdb.cpp:77-86) become X = alphabet-1, as runFilterOnCpu treats masked
 // residues (ungappedprefilter.cpp:401-404); mask_from = 256 disables that.  The re-layout (16-byte aligned, padded with code
 // `alphabet`) runs on all host threads: at 20 M sequences this is 7.5 GB of bytes.
-static int db_load_impl(b200_ctx *ctx, const uint8_t *base, const uint64_t *starts, const int32_t *lens, uint64_t n_seq, int alphabet,
-                        int mask_from, uint64_t n_res) {
+int b200_db_load_impl(b200_ctx *ctx, const uint8_t *base, const uint64_t *starts, const int32_t *lens, uint64_t n_seq, int alphabet,
+                      int mask_from, uint64_t n_res) {
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     db_free(ctx);
     std::vector<uint64_t> h_off(n_seq);
@@ -1249,7 +1257,7 @@ int b200_db_load(b200_ctx *ctx, const uint8_t *residues, const uint64_t *offsets
         if (l > 65535) return set_err(ctx, B200_ERR_RANGE, "b200_db_load: sequence longer than 65535 (maxSeqLen)");
         lens[i] = (int32_t) l;
     }
-    return db_load_impl(ctx, residues, offsets, lens.data(), n_seq, alphabet, 256, offsets[n_seq] - offsets[0]);
+    return b200_db_load_impl(ctx, residues, offsets, lens.data(), n_seq, alphabet, 256, offsets[n_seq] - offsets[0]);
 }
 
 int b200_db_load_padded(b200_ctx *ctx, const uint8_t *data, const size_t *offsets, const int32_t *lengths, uint64_t n_seq, int alphabet) {
@@ -1265,7 +1273,7 @@ int b200_db_load_padded(b200_ctx *ctx, const uint8_t *data, const size_t *offset
         starts[i] = offsets[i];
         n_res += (uint64_t) lengths[i];
     }
-    return db_load_impl(ctx, data, starts.data(), lengths, n_seq, alphabet, 32, n_res);
+    return b200_db_load_impl(ctx, data, starts.data(), lengths, n_seq, alphabet, 32, n_res);
 }
 
 int b200_device_count(void) {
@@ -1395,40 +1403,72 @@ int b200_ungapped_scan(b200_ctx *ctx, const b200_query *queries, int nq, int min
 }
 
 // ---- A1 ---------------------------------------------------------------------------------------------
-int b200_diag_score(b200_ctx *ctx, const b200_query *q, const uint32_t *ids, const uint16_t *diagonals, uint64_t n,
-                    uint8_t *counts, int32_t *raw) {
+// Many queries' hit lists in one call: one upload of all profiles and hits, one launch, one download, one synchronisation --
+// what QueryMatcher's OpenMP threads need so that they do not serialise on a per-query round trip (QueryMatcher.cpp:73,131).
+// queries[i] owns hits [hit_offsets[i], hit_offsets[i+1]).
+int b200_diag_score_batch(b200_ctx *ctx, const b200_query *queries, int nq, const uint64_t *hit_offsets, const uint32_t *ids,
+                          const uint16_t *diagonals, uint8_t *counts, int32_t *raw) {
     if (ctx == nullptr) return B200_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (ctx->n_seq == 0) return set_err(ctx, B200_ERR_NODB, "no target DB loaded");
-    if (q == nullptr || q->profile == nullptr || q->qlen <= 0 || ids == nullptr || diagonals == nullptr || counts == nullptr)
-        return set_err(ctx, B200_ERR_ARG, "b200_diag_score: bad arguments");
-    if (q->qlen >= 32768 || ctx->max_len >= 32768)
-        return set_err(ctx, B200_ERR_RANGE, "b200_diag_score: sequences >= 32768 take the reference's computeLongScore path (T6)");
+    if (ctx->alphabet > 31) return set_err(ctx, B200_ERR_ARG, "b200_diag_score: the resident DB is an ASCII DB (b200_db_load_ascii)");
+    if (queries == nullptr || nq <= 0 || hit_offsets == nullptr) return set_err(ctx, B200_ERR_ARG, "b200_diag_score: bad arguments");
+    const uint64_t n = hit_offsets[nq] - hit_offsets[0];
     if (n == 0) return B200_OK;
+    if (ids == nullptr || diagonals == nullptr || counts == nullptr) return set_err(ctx, B200_ERR_ARG, "b200_diag_score: bad arguments");
+    if (ctx->max_len >= 32768)
+        return set_err(ctx, B200_ERR_RANGE, "b200_diag_score: sequences >= 32768 take the reference's computeLongScore path (T6)");
+    std::vector<DiagQuery> h_dq(nq);
+    uint64_t pbytes = 0;
+    for (int i = 0; i < nq; i++) {
+        if (queries[i].profile == nullptr || queries[i].qlen <= 0 || hit_offsets[i + 1] < hit_offsets[i])
+            return set_err(ctx, B200_ERR_ARG, "b200_diag_score: query without profile, or hit offsets not monotone");
+        if (queries[i].qlen >= 32768)
+            return set_err(ctx, B200_ERR_RANGE, "b200_diag_score: sequences >= 32768 take the reference's computeLongScore path (T6)");
+        h_dq[i].prof_off = pbytes; h_dq[i].hit_begin = hit_offsets[i] - hit_offsets[0]; h_dq[i].qlen = queries[i].qlen; h_dq[i].pad_ = 0;
+        pbytes += round_up((uint64_t) ctx->alphabet * queries[i].qlen, 16);
+    }
+    const uint32_t *idp = ids + hit_offsets[0];
+    const uint16_t *dgp = diagonals + hit_offsets[0];
+    uint8_t *cnp = counts + hit_offsets[0];
+    int32_t *rwp = raw ? raw + hit_offsets[0] : nullptr;
     for (uint64_t i = 0; i < n; i++)
-        if (ids[i] >= ctx->n_seq) return set_err(ctx, B200_ERR_ARG, "b200_diag_score: target id out of range");
+        if (idp[i] >= ctx->n_seq) return set_err(ctx, B200_ERR_ARG, "b200_diag_score: target id out of range");
     CU_TRY(ctx, cudaSetDevice(ctx->device));
-    const size_t pbytes = (size_t) ctx->alphabet * q->qlen;
+    std::vector<int8_t> h_prof(pbytes);
+    for (int i = 0; i < nq; i++) memcpy(h_prof.data() + h_dq[i].prof_off, queries[i].profile, (size_t) ctx->alphabet * queries[i].qlen);
     CU_TRY(ctx, ctx->raw.reserve(pbytes));
+    CU_TRY(ctx, ctx->qdesc.reserve(sizeof(DiagQuery) * nq));
     CU_TRY(ctx, ctx->ids.reserve(n * sizeof(uint32_t)));
     CU_TRY(ctx, ctx->diags.reserve(n * sizeof(uint16_t)));
     CU_TRY(ctx, ctx->counts.reserve(n));
     if (raw) CU_TRY(ctx, ctx->rawout.reserve(n * sizeof(int32_t)));
-    CU_TRY(ctx, cudaMemcpyAsync(ctx->raw.p, q->profile, pbytes, cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(ctx, cudaMemcpyAsync(ctx->ids.p, ids, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(ctx, cudaMemcpyAsync(ctx->diags.p, diagonals, n * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
-    CU_TRY(ctx, cudaMemcpyAsync(ctx->counts.p, counts, n, cudaMemcpyHostToDevice, ctx->stream));
-    const uint64_t warps = (n + 0) ;
-    const unsigned ctas = (unsigned) std::min<uint64_t>((warps + 7) / 8, (uint64_t) ctx->sm_count * 8);
-    diag_score_kernel<<<ctas, 256, 0, ctx->stream>>>(ctx->raw.as<int8_t>(), q->qlen, ctx->d_res, ctx->d_off, ctx->d_len,
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->raw.p, h_prof.data(), pbytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->qdesc.p, h_dq.data(), sizeof(DiagQuery) * nq, cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->ids.p, idp, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->diags.p, dgp, n * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(ctx->counts.p, cnp, n, cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned ctas = (unsigned) std::min<uint64_t>((n + 7) / 8, (uint64_t) ctx->sm_count * 8);
+    CU_TRY(ctx, cudaEventRecord(ctx->ev[12], ctx->stream));
+    diag_score_kernel<<<ctas, 256, 0, ctx->stream>>>(ctx->raw.as<int8_t>(), ctx->qdesc.as<DiagQuery>(), nq, ctx->d_res, ctx->d_off, ctx->d_len,
                                                      ctx->ids.as<uint32_t>(), ctx->diags.as<uint16_t>(), n,
                                                      ctx->counts.as<uint8_t>(), raw ? ctx->rawout.as<int32_t>() : nullptr);
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
-    CU_TRY(ctx, cudaMemcpyAsync(counts, ctx->counts.p, n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (raw) CU_TRY(ctx, cudaMemcpyAsync(raw, ctx->rawout.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU_TRY(ctx, cudaEventRecord(ctx->ev[13], ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(cnp, ctx->counts.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (raw) CU_TRY(ctx, cudaMemcpyAsync(rwp, ctx->rawout.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev[12], ctx->ev[13]);
     return B200_OK;
+}
+
+int b200_diag_score(b200_ctx *ctx, const b200_query *q, const uint32_t *ids, const uint16_t *diagonals, uint64_t n,
+                    uint8_t *counts, int32_t *raw) {
+    if (ctx == nullptr) return B200_ERR_ARG;
+    if (q == nullptr) return set_err(ctx, B200_ERR_ARG, "b200_diag_score: bad arguments");
+    const uint64_t offs[2] = {0, n};
+    return b200_diag_score_batch(ctx, q, 1, offs, ids, diagonals, counts, raw);
 }
 
 // ---- A3-A5 ------------------------------------------------------------------------------------------

@@ -96,6 +96,11 @@ struct b200_ctx {
     uint64_t n_seq = 0, n_res = 0;
     int alphabet = 0;
     int max_len = 0;
+    // resident ASCII copy of a sequence DB for rescorediagonal (b200_db_load_ascii): bytes as stored, concatenated
+    uint8_t *d_ares = nullptr;
+    uint64_t *d_aoff = nullptr;   // [n_aseq + 1]
+    uint64_t n_aseq = 0;
+    std::vector<uint64_t> h_aoff;
     // scratch
     DevBuf raw, pad, qdesc, dense, hits, nhits, pairs, items, out4, bnd, ids, diags, counts, rawout, counter;
 };
@@ -106,5 +111,11 @@ static inline int b200_set_err(b200_ctx *ctx, int code, const char *msg) { ctx->
 int b200_sw_backtrace_impl(b200_ctx *ctx, const b200_query *queries, const uint8_t *const *query_seqs, int nq, const b200_pair *pairs,
                            uint64_t n, int gap_open, int gap_extend, const b200_sw_aln *alns, b200_sw_bt *out, uint32_t *cigars,
                            const uint64_t *cigar_offsets, std::vector<uint32_t> *pool_out, std::vector<uint64_t> *base_out);
+
+// common body of b200_db_load / b200_db_load_padded / b200_db_load_ascii (b200_align.cu); the caller holds ctx->mu
+int b200_db_load_impl(b200_ctx *ctx, const uint8_t *base, const uint64_t *starts, const int32_t *lens, uint64_t n_seq, int alphabet,
+                      int mask_from, uint64_t n_res);
+
+void b200_ascii_db_free(b200_ctx *ctx);   // b200_rescore.cu
 
 #endif  // B200_INTERNAL_H

@@ -60,6 +60,17 @@ int main(int argc, char **argv) {
     b200::Marv::Stats st = marv.scan((const char *) q.data(), qlen, pssm.data(), results.data(), sw.bias());
     out.push_back((int32_t) st.results);
     for (size_t i = 0; i < 50; i++) { out.push_back(i < st.results ? (int32_t) results[i].id : -1); out.push_back(i < st.results ? results[i].score : -1); }
+    // --- Marv in GAPLESS_SMITH_WATERMAN mode (search --gpu 1 --alignment-mode 1): gapped score + end positions of the best ungapped hits
+    b200::Marv marv2(&dev, nT, A, 0, 50, b200::Marv::GAPLESS_SMITH_WATERMAN);
+    marv2.setMinScore(15);
+    std::vector<b200::Marv::Result> results2(50);
+    b200::Marv::Stats st2 = marv2.scan((const char *) q.data(), qlen, pssm.data(), results2.data(), sw.bias());
+    out.push_back((int32_t) st2.results);
+    for (size_t i = 0; i < 50; i++) {
+        const bool on = i < st2.results;
+        out.push_back(on ? (int32_t) results2[i].id : -1); out.push_back(on ? results2[i].score : -1);
+        out.push_back(on ? results2[i].qEndPos : -1); out.push_back(on ? results2[i].dbEndPos : -1);
+    }
     // --- UngappedAlignment-style
     b200::UngappedAlignment ua(&dev, mat.data(), A);
     std::vector<float> fb(qlen);

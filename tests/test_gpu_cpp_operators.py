@@ -62,6 +62,17 @@ def test_operator_mirror_matches_oracle(tmp_path, built_lib, oracle, blosum):
     ids_e = ids_e[order][:50]
     assert n_scan == len(ids_e)
     assert np.array_equal(scan[:n_scan, 0], ids_e) and np.array_equal(scan[:n_scan, 1], dense[ids_e])
+    # GAPLESS_SMITH_WATERMAN: the same 50 targets, rescored with the gapped kernel, ordered (gapped score desc, id asc)
+    n_gsw = rest[101]
+    gsw = rest[102:302].reshape(50, 4)
+    assert n_gsw == n_scan
+    from oracle.pyoracle import pack_targets
+    sd, so = pack_targets([res[int(to[t]):int(to[t + 1])] for t in ids_e])
+    e = oracle.sw_score_endpos(q, cb, bias, sd, so)
+    order2 = np.lexsort((ids_e, -e[:, 0]))
+    exp_gsw = np.stack([ids_e[order2], e[order2, 0], e[order2, 1], e[order2, 2]], 1)
+    assert np.array_equal(gsw[:n_gsw], exp_gsw)
+    rest = rest[201:]
     counts = rest[101:101 + nh]
     c_exp, _ = oracle.diag(q, oracle.round_bias_diag(oracle.comp_bias(q)), res, to, ids, dg)
     assert np.array_equal(counts, c_exp.astype(np.int32))
