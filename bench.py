@@ -432,24 +432,46 @@ def main():
         gather_hit_lists(hits_np, nh, args.queries_per_step, dist, device=torch.device("cuda", local_rank))
 
     # ---- value: resident inputs, device-timed -------------------------------------------------------
-    for s in range(args.warmup):
-        jobs[s % n_distinct].run()
-        h, nh, _ = jobs[s % n_distinct].fetch()
-        gather_hits(h, nh)
+    # N=1: scans back to back on the library's stream, CUDA events around the loop.
+    # N>1: the same, plus per step the hit lists of every rank gathered with one NCCL all_gather -- pipelined: two scans stay in flight
+    #      while the lists of the oldest finished step are downloaded (on the job's own event) and gathered on a second stream.
+    pipe_jobs = jobs if dist is None else jobs + [ctx.scan_job(batches[0], 15, args.max_hits)]
+    pipe_cells = cells_per_step if dist is None else cells_per_step + [cells_per_step[0]]
+    gather = None
+    if dist is not None:
+        from mmseqs2_b200.sharding import HitGather
+        gather = HitGather(args.queries_per_step, args.max_hits, dist, torch.device("cuda", local_rank))
+    npj = len(pipe_jobs)
+
+    def run_steps(n_steps):
+        cells = 0
+        if dist is None:
+            for s in range(n_steps):
+                pipe_jobs[s % npj].run()
+                cells += pipe_cells[s % npj]
+            return cells
+        depth = 2
+        for s in range(min(depth, n_steps)):
+            pipe_jobs[s % npj].run()
+        for s in range(n_steps):
+            h, nh, _ = pipe_jobs[s % npj].fetch()          # waits for step s only
+            if s + depth < n_steps:
+                pipe_jobs[(s + depth) % npj].run()         # its buffers were read out one iteration ago
+            if len(gather.started) >= 2:
+                gather.finish()
+            gather.start(h, nh)
+            cells += pipe_cells[s % npj]
+        gather.drain()
+        return cells
+
+    run_steps(args.warmup)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = ctx.launches
     ctx.event_record(0)
     t_wall0 = time.perf_counter()
-    total_cells = 0
-    for s in range(args.steps):
-        j = jobs[s % n_distinct]
-        j.run()
-        total_cells += cells_per_step[s % n_distinct]
-        if dist is not None:
-            h, nh, _ = j.fetch()
-            gather_hits(h, nh)
+    total_cells = run_steps(args.steps)
     ctx.event_record(1)
     barrier()
     t_wall = time.perf_counter() - t_wall0

@@ -113,7 +113,12 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
     static_assert(!TILED || G == 32, "the tiled (long-query) variant runs one target per warp");
     constexpr int C = K / 4;           // full uint4 chunks of a lane's K registers ...
     constexpr int T = (K % 4) / 2;     // ... plus one uint2 tail chunk when K = 4C + 2
-    constexpr int ROW_W = G * K;       // 32-bit words per residue row: [c][g] uint4, then [g] uint2
+    // 32-bit words per residue row: [c][g] uint4, then [g] uint2.  With G = 8 a half-warp (the unit of an LDS.64) holds two
+    // groups, i.e. two residue rows: their 64-byte tail chunks would land on the same 16 banks whenever the rows differ by an
+    // even number (r01 ncu: 3-4 % of all wavefronts of <8,22>/<8,26> were such conflicts).  A second copy of the tail 16 words
+    // further on, read by the odd groups, puts the two on disjoint bank halves; the row stride becomes 32(C+1) words, a multiple of 32.
+    constexpr int TAIL2 = (G == 8 && T == 1) ? 16 : 0;
+    constexpr int ROW_W = G * K + TAIL2;
     extern __shared__ uint4 smem_u4[];
     uint32_t *P = reinterpret_cast<uint32_t *>(smem_u4);
     uint32_t *Pp = P + (size_t) (A + 1) * ROW_W;
@@ -125,6 +130,7 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
     const uint32_t warps_per_cta = blockDim.x >> 5;
     const uint32_t warp_in_cta = threadIdx.x >> 5;
     const uint32_t padword = (uint32_t) A * 0x01010101u;
+    const int tail_off = 4 * C * G + (TAIL2 ? ((lane >> 3) & 1) * TAIL2 : 0);   // which copy of the tail chunk this group reads
     int cur_q = -1;
     uint32_t cst = 0;
 
@@ -169,6 +175,7 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
             const int dst = a * ROW_W + (r < 4 * C ? ((r >> 2) * G + gg) * 4 + (r & 3) : 4 * C * G + gg * 2 + (r - 4 * C));
             Pw[dst] = pack16(s0, s1);
             Ppw[dst] = pack16(sm1, s0);
+            if (TAIL2 && r >= 4 * C) { Pw[dst + TAIL2] = pack16(s0, s1); Ppw[dst + TAIL2] = pack16(sm1, s0); }
         }
         cst = (uint32_t) (255 - q.bias) * 0x00010001u;
         cur_q = qi;
@@ -222,7 +229,7 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
                         S[4 * c + 3] = __viaddmin_s16x2_relu(S[4 * c + 3], x.w, cst);
                     }
                     if (T) {
-                        const uint2 x = reinterpret_cast<const uint2 *>(prow + 4 * C * G)[g];
+                        const uint2 x = reinterpret_cast<const uint2 *>(prow + tail_off)[g];
                         S[4 * C + 0] = __viaddmin_s16x2_relu(S[4 * C + 0], x.x, cst);
                         S[4 * C + 1] = __viaddmin_s16x2_relu(S[4 * C + 1], x.y, cst);
                     }
@@ -239,7 +246,7 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
 #pragma unroll
                     for (int c = 0; c < C; c++) x[c] = p[c * G];
                     if (T) {
-                        const uint2 xt = reinterpret_cast<const uint2 *>(prow + 4 * C * G)[g];
+                        const uint2 xt = reinterpret_cast<const uint2 *>(prow + tail_off)[g];
                         S[4 * C + 1] = __viaddmin_s16x2_relu(S[4 * C + 0], xt.y, cst);
                         S[4 * C + 0] = __viaddmin_s16x2_relu(C > 0 ? S[4 * C - 1] : carry, xt.x, cst);
                     }
@@ -957,9 +964,11 @@ struct ScanCfg { int G, K; };
 const ScanCfg kScanCfgs[] = {B200_SCAN_CFGS(B200_SCAN_ENTRY)};
 #undef B200_SCAN_ENTRY
 
+constexpr int kScanCounters = 64;   // one work-unit counter per launch of a batch (launches of one batch may run concurrently)
+
 template <int G, int K, bool TILED>
-cudaError_t launch_scan_cfg(b200_ctx *ctx, const int8_t *raw, const QueryDesc *qd, int nq, uint8_t *dense) {
-    const size_t smem = (size_t) 2 * (ctx->alphabet + 1) * K * G * sizeof(uint32_t);
+cudaError_t launch_scan_cfg(b200_ctx *ctx, const int8_t *raw, const QueryDesc *qd, int nq, uint8_t *dense, cudaStream_t stream, int counter_slot) {
+    const size_t smem = (size_t) 2 * (ctx->alphabet + 1) * (K * G + ((G == 8 && K % 4 == 2) ? 16 : 0)) * sizeof(uint32_t);
     cudaError_t e = cudaFuncSetAttribute(ungapped_scan_kernel<G, K, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -974,28 +983,29 @@ cudaError_t launch_scan_cfg(b200_ctx *ctx, const int8_t *raw, const QueryDesc *q
     if (TILED) unit_targets = std::min<uint64_t>(unit_targets, 4 * groups_per_cta);   // bounds the tile-boundary scratch
     const uint32_t units_per_query = (uint32_t) ((ctx->n_seq + unit_targets - 1) / unit_targets);
     const uint64_t ctas = std::max<uint64_t>(1, std::min<uint64_t>(resident, (uint64_t) units_per_query * nq));
-    e = ctx->counter.reserve(sizeof(unsigned));
-    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->counter.p, 0, sizeof(unsigned), ctx->stream);
+    e = ctx->counter.reserve(sizeof(unsigned) * kScanCounters);
+    unsigned *counter = ctx->counter.as<unsigned>() + counter_slot;
+    if (e == cudaSuccess) e = cudaMemsetAsync(counter, 0, sizeof(unsigned), stream);
     uint32_t slot_words = 0;
     if (TILED && e == cudaSuccess) {
         slot_words = (uint32_t) (round_up((uint64_t) ctx->max_len, 16) / 2 + 8);
         e = ctx->bnd.reserve(sizeof(uint32_t) * (size_t) slot_words * unit_targets * ctas);
     }
     if (e != cudaSuccess) return e;
-    ungapped_scan_kernel<G, K, TILED><<<(unsigned) ctas, 256, smem, ctx->stream>>>(
+    ungapped_scan_kernel<G, K, TILED><<<(unsigned) ctas, 256, smem, stream>>>(
         raw, qd, ctx->d_res, ctx->d_off, ctx->d_len, ctx->d_order, (uint32_t) ctx->n_seq, ctx->alphabet, dense, (uint32_t) nq, units_per_query,
-        (uint32_t) unit_targets, ctx->counter.as<unsigned>(), TILED ? ctx->bnd.as<uint32_t>() : nullptr, slot_words);
+        (uint32_t) unit_targets, counter, TILED ? ctx->bnd.as<uint32_t>() : nullptr, slot_words);
     ctx->launches++;
     return cudaGetLastError();
 }
 
 // queries of one launch must share a (G,K) configuration; the caller groups them by capacity class
-cudaError_t launch_scan(b200_ctx *ctx, int cfg, const int8_t *raw, const QueryDesc *qd, int nq, uint8_t *dense) {
+cudaError_t launch_scan(b200_ctx *ctx, int cfg, const int8_t *raw, const QueryDesc *qd, int nq, uint8_t *dense, cudaStream_t stream, int counter_slot) {
     switch (cfg) {
-#define B200_SCAN_CASE(n, g, k) case n: return launch_scan_cfg<g, k, false>(ctx, raw, qd, nq, dense);
+#define B200_SCAN_CASE(n, g, k) case n: return launch_scan_cfg<g, k, false>(ctx, raw, qd, nq, dense, stream, counter_slot);
         B200_SCAN_CFGS(B200_SCAN_CASE)
 #undef B200_SCAN_CASE
-        default: return launch_scan_cfg<32, 32, true>(ctx, raw, qd, nq, dense);   // queries longer than 2047: row tiles of 2048
+        default: return launch_scan_cfg<32, 32, true>(ctx, raw, qd, nq, dense, stream, counter_slot);   // queries longer than 2047: row tiles of 2048
     }
 }
 
@@ -1083,7 +1093,10 @@ struct b200_job {
         int max_Lp = 0;
     };
     std::vector<Part *> parts;
+    cudaEvent_t done = nullptr;   // recorded on the ctx stream behind the job's last kernel
+    bool ran = false;
     void free_all() {
+        if (done) { cudaEventDestroy(done); done = nullptr; }
         for (Part *pt : parts) { pt->pairs.release(); pt->items.release(); pt->out.release(); delete pt; }
         parts.clear();
         raw.release(); qdesc.release(); qdesc_grouped.release(); dense.release(); hits.release(); nhits.release();
@@ -1100,8 +1113,12 @@ int b200_create(int device, b200_ctx **out) {
     ctx->device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 3 && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return B200_ERR_CUDA; }
     for (int i = 0; i < 16; i++) cudaEventCreate(&ctx->ev[i]);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    for (int i = 0; i < 3; i++) cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     ctx->sm_count = prop.multiProcessorCount;
@@ -1131,6 +1148,9 @@ void b200_destroy(b200_ctx *ctx) {
                       &ctx->out4, &ctx->bnd, &ctx->ids, &ctx->diags, &ctx->counts, &ctx->rawout, &ctx->counter};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
+    cudaEventDestroy(ctx->ev_fork);
+    for (int i = 0; i < 3; i++) { cudaEventDestroy(ctx->ev_join[i]); cudaStreamDestroy(ctx->side[i]); }
+    cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1339,24 +1359,52 @@ int b200_scan_job_create(b200_ctx *ctx, const b200_query *queries, int nq, int m
     return B200_OK;
 }
 
+// The capacity classes present in a batch are independent launches over disjoint output rows.  They go out on the ctx stream and up
+// to three side streams, largest class first: every launch is a persistent grid that fills the GPU, so a later class only gets SM
+// slots as the CTAs of an earlier one run out of work units -- its start overlaps the earlier launch's tail instead of waiting for
+// the last CTA (previously: one idle tail per class, five per 16-query step of config[1]).  The tiled long-query variant shares
+// one boundary scratch and stays on the ctx stream.
 static int scan_job_run_locked(b200_job *job) {
     b200_ctx *ctx = job->ctx;
+    struct L { int cfg, pos, n; };
+    std::vector<L> launches;
     int pos = 0;
     for (size_t c = 0; c < job->cfg_groups.size(); c++) {
         const int n = (int) job->cfg_groups[c].size();
-        if (n == 0) continue;
         // grid.y is limited to 65535
-        for (int s = 0; s < n; s += 32768) {
-            const int m = std::min(32768, n - s);
-            CU_TRY(ctx, launch_scan(ctx, (int) c, job->raw.as<int8_t>(), job->qdesc.as<QueryDesc>() + pos + s, m,
-                                    job->dense.as<uint8_t>() + (size_t) (pos + s) * ctx->n_seq));
-        }
+        for (int s = 0; s < n; s += 32768) launches.push_back({(int) c, pos + s, std::min(32768, n - s)});
         pos += n;
     }
+    const int n_cfg = (int) (sizeof(kScanCfgs) / sizeof(kScanCfgs[0]));
+    auto weight = [n_cfg](const L &l) { return (double) l.n * (l.cfg < n_cfg ? 2.0 * kScanCfgs[l.cfg].G * kScanCfgs[l.cfg].K : 1e9); };
+    std::stable_sort(launches.begin(), launches.end(), [&weight](const L &a, const L &b) { return weight(a) > weight(b); });
+    const bool fan_out = launches.size() > 1 && getenv("B200_SCAN_SERIAL") == nullptr;
+    if (fan_out) CU_TRY(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    bool used[3] = {false, false, false};
+    int next_side = 0;
+    for (size_t i = 0; i < launches.size(); i++) {
+        const L &l = launches[i];
+        cudaStream_t st = ctx->stream;
+        if (fan_out && i > 0 && l.cfg < n_cfg && i < (size_t) kScanCounters) {
+            const int k = next_side++ % 3;
+            st = ctx->side[k];
+            if (!used[k]) { CU_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_fork, 0)); used[k] = true; }
+        }
+        CU_TRY(ctx, launch_scan(ctx, l.cfg, job->raw.as<int8_t>(), job->qdesc.as<QueryDesc>() + l.pos, l.n,
+                                job->dense.as<uint8_t>() + (size_t) l.pos * ctx->n_seq, st, (int) (i % kScanCounters)));
+    }
+    for (int k = 0; k < 3; k++)
+        if (used[k]) {
+            CU_TRY(ctx, cudaEventRecord(ctx->ev_join[k], ctx->side[k]));
+            CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0));
+        }
     topk_select_kernel<<<job->nq, 1024, 0, ctx->stream>>>(job->dense.as<uint8_t>(), (uint32_t) ctx->n_seq, job->thr, job->k,
                                                           job->hits.as<b200_hit>(), job->nhits.as<uint32_t>());
     ctx->launches++;
     CU_TRY(ctx, cudaGetLastError());
+    if (job->done == nullptr) CU_TRY(ctx, cudaEventCreateWithFlags(&job->done, cudaEventDisableTiming));
+    CU_TRY(ctx, cudaEventRecord(job->done, ctx->stream));
+    job->ran = true;
     return B200_OK;
 }
 
@@ -1369,15 +1417,19 @@ int b200_scan_job_fetch(b200_job *job, b200_hit *hits, uint32_t *n_hits, uint8_t
     const uint32_t k = job->k;
     std::vector<b200_hit> h_hits((size_t) nq * k);
     std::vector<uint32_t> h_n(nq);
-    CU_TRY(ctx, cudaMemcpyAsync(h_n.data(), job->nhits.p, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(ctx, cudaMemcpyAsync(h_hits.data(), job->hits.p, sizeof(b200_hit) * nq * k, cudaMemcpyDeviceToHost, ctx->stream));
+    // The download waits for THIS job's last kernel only (its event), on the copy stream: jobs enqueued after it keep the GPU busy
+    // while the host collects -- what lets a caller overlap the hit-list gather of step s with the scan of step s+1.
+    cudaStream_t cs = job->ran ? ctx->copy_stream : ctx->stream;
+    if (job->ran) CU_TRY(ctx, cudaStreamWaitEvent(cs, job->done, 0));
+    CU_TRY(ctx, cudaMemcpyAsync(h_n.data(), job->nhits.p, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost, cs));
+    CU_TRY(ctx, cudaMemcpyAsync(h_hits.data(), job->hits.p, sizeof(b200_hit) * nq * k, cudaMemcpyDeviceToHost, cs));
     if (dense != nullptr) {
         for (int pos = 0; pos < nq; pos++)
             CU_TRY(ctx, cudaMemcpyAsync(dense + (size_t) job->grouped_order[pos] * ctx->n_seq,
                                         job->dense.as<uint8_t>() + (size_t) pos * ctx->n_seq, ctx->n_seq,
-                                        cudaMemcpyDeviceToHost, ctx->stream));
+                                        cudaMemcpyDeviceToHost, cs));
     }
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_TRY(ctx, cudaStreamSynchronize(cs));
     for (int pos = 0; pos < nq; pos++) {
         const int qi = job->grouped_order[pos];
         const uint32_t n = std::min(h_n[pos], k);

@@ -79,6 +79,9 @@ struct DevBuf {  // grow-only device scratch
 struct b200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // result downloads of resident jobs: waits on the job's own event, not on later launches
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // the capacity classes of one scan batch run on stream + side[] concurrently
+    cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev[16];
     std::mutex mu;
     std::string err;

@@ -48,6 +48,68 @@ def gather_hit_lists(hits, n_hits, max_queries_per_rank, dist=None, device=None)
     return hb, cn
 
 
+class HitGather:
+    """The same exchange, pipelined: start(step s) enqueues pinned-host -> device, one all_gather_into_tensor (NCCL over NVLink) and the
+    copy back on a high-priority stream of its own and returns at once; finish() hands out the gathered lists of the oldest started
+    step.  The caller keeps two scans in flight on the library's stream meanwhile, so the collective (a few hundred KB) and its
+    host-side staging never sit between two scans.  Fixed-size records: [max_q][k][2] int32 + [max_q] counts per rank."""
+
+    def __init__(self, max_queries_per_rank, k, dist, device, depth=3):
+        import torch
+        self.torch, self.dist, self.device = torch, dist, device
+        self.mq, self.k = max_queries_per_rank, k
+        self.world = dist.get_world_size()
+        self.n = self.mq * self.k * 2 + self.mq
+        self.cuda = device is not None and torch.device(device).type == "cuda"     # CPU (gloo) path: same protocol, for the tests
+        self.stream = torch.cuda.Stream(device=device, priority=-1) if self.cuda else None
+        self.slots = []
+        for _ in range(depth):
+            h_in, h_out = torch.zeros(self.n, dtype=torch.int32), torch.zeros(self.world * self.n, dtype=torch.int32)
+            self.slots.append({"h_in": h_in.pin_memory() if self.cuda else h_in,
+                               "d_in": torch.zeros(self.n, dtype=torch.int32, device=device) if self.cuda else None,
+                               "d_out": torch.zeros(self.world * self.n, dtype=torch.int32, device=device) if self.cuda else None,
+                               "h_out": h_out.pin_memory() if self.cuda else h_out,
+                               "ev": torch.cuda.Event() if self.cuda else None, "work": None})
+        self.started, self.head = [], 0
+
+    def start(self, hits, n_hits):
+        torch = self.torch
+        sl = self.slots[self.head % len(self.slots)]
+        self.head += 1
+        buf = sl["h_in"].numpy()
+        buf[:] = 0
+        nq = hits.shape[0]
+        if nq:
+            buf[:self.mq * self.k * 2].reshape(self.mq, self.k, 2)[:nq] = hits.view(np.int32).reshape(nq, self.k, 2)
+            buf[self.mq * self.k * 2:][:nq] = n_hits
+        if self.cuda:
+            with torch.cuda.stream(self.stream):
+                sl["d_in"].copy_(sl["h_in"], non_blocking=True)
+                self.dist.all_gather_into_tensor(sl["d_out"], sl["d_in"])
+                sl["h_out"].copy_(sl["d_out"], non_blocking=True)
+                sl["ev"].record(self.stream)
+        else:
+            outs = list(sl["h_out"].view(self.world, self.n).unbind(0))
+            sl["work"] = self.dist.all_gather(outs, sl["h_in"], async_op=True)
+        self.started.append(sl)
+
+    def finish(self):
+        """-> (hits_all [world][max_q][k][2], n_all [world][max_q]) of the oldest started step"""
+        sl = self.started.pop(0)
+        if self.cuda:
+            sl["ev"].synchronize()
+        else:
+            sl["work"].wait()
+        flat = sl["h_out"].numpy().reshape(self.world, self.n).copy()     # the slot is reused by a later start()
+        return flat[:, :self.mq * self.k * 2].reshape(self.world, self.mq, self.k, 2), flat[:, self.mq * self.k * 2:]
+
+    def drain(self):
+        out = None
+        while self.started:
+            out = self.finish()
+        return out
+
+
 def merge_target_sharded(hits, n_hits, id_offset, k, dist=None, device=None):
     """The other split of SURVEY 8e, for a DB too large for one GPU: every rank holds a slice of the TARGETS (its local ids start
     at id_offset in the global numbering) and has scanned all queries against it.  hits [nq][k_local] / n_hits [nq] are the local

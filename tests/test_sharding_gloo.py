@@ -126,3 +126,45 @@ def test_target_sharded_merge_equals_unsharded_topk():
         assert nm[i] == len(ids)
         assert [m[0] for m in merged[i][:nm[i]]] == ids.tolist() and [m[1] for m in merged[i][:nm[i]]] == sc.tolist()
 
+
+
+# ---- pipelined gather (what bench.py --gpus N runs per step): several steps in flight, results in start order ------------------------
+def _pipe_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mmseqs2_b200.sharding import HitGather
+    g = HitGather(5, K, dist, None)
+    out = []
+    for step in range(6):
+        hits, n = fake_scan([100 * step + 10 * rank + i for i in range(3 + rank)])     # ranks hold different numbers of queries
+        if len(g.started) >= 2:
+            out.append(g.finish())
+        g.start(hits, n)
+    while g.started:
+        out.append(g.finish())
+    if rank == 0:
+        ret.put([(hb.tolist(), cn.tolist()) for hb, cn in out])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pipelined_gather_keeps_step_order_and_content():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_pipe_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    steps = ret.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert len(steps) == 6
+    for step, (hb, cn) in enumerate(steps):
+        hb, cn = np.array(hb), np.array(cn)
+        for rank in range(2):
+            hits, n = fake_scan([100 * step + 10 * rank + i for i in range(3 + rank)])
+            assert cn[rank, :3 + rank].tolist() == n.tolist() and (cn[rank, 3 + rank:] == 0).all()
+            for i in range(3 + rank):
+                assert hb[rank, i, :n[i]].tolist() == hits[i, :n[i]].view(np.int32).reshape(-1, 2).tolist()
