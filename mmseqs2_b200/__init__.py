@@ -7,6 +7,7 @@ There is no CPU fallback: importing the device API without the built library rai
 from .api import (  # noqa: F401
     B200Error,
     Context,
+    MultiContext,
     QueryProfile,
     SubMatrix,
     lib_path,

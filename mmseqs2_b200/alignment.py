@@ -123,9 +123,10 @@ def align_batch(ctx, submat, queries, hit_lists, params, evalue, query_keys=None
                 ids = np.minimum(np.asarray(hit_lists[qi], np.int64), len(lens) - 1)   # range errors are the library's to report
                 bt_cap += int(len(queries[qi]) * len(hit_lists[qi]) + lens[ids].sum())
     pool = np.empty(bt_cap, np.uint8)            # written by the library up to the last accepted backtrace; never read beyond
-    rc = lib.b200_align_batch(ctx.h, _p(mat), _p(pb), int(submat.A), _p(qres), _p(qoff), _p(qk), ctypes.c_uint32(nq), _p(hoff), _p(htg),
-                              _p(tk), ctypes.byref(params), ctypes.byref(evalue), _p(res), _p(nres), _p(pool), _u64(bt_cap),
-                              ctypes.byref(n_aln))
+    fn = lib.b200_multi_align_batch if type(ctx).__name__ == "MultiContext" else lib.b200_align_batch   # same arguments, several GPUs
+    rc = fn(ctx.h, _p(mat), _p(pb), int(submat.A), _p(qres), _p(qoff), _p(qk), ctypes.c_uint32(nq), _p(hoff), _p(htg),
+            _p(tk), ctypes.byref(params), ctypes.byref(evalue), _p(res), _p(nres), _p(pool), _u64(bt_cap),
+            ctypes.byref(n_aln))
     ctx._check(rc)
     out = [res[int(hoff[i]):int(hoff[i]) + int(nres[i])] for i in range(nq)]
     return out, pool, int(n_aln.value)

@@ -419,3 +419,58 @@ class Context:
         h = _vp()
         self._check(self.lib.b200_sw_job_create(self.h, cq, len(queries), _p(pa), _u64(len(pa)), go, ge, ctypes.byref(h)))
         return Job(self, h, "sw", n=len(pa))
+
+
+class MultiContext:
+    """Several GPUs of a node behind one handle (include/b200_multi.h): query-sharded (DB replicated) or target-sharded."""
+
+    def __init__(self, devices=None):
+        self.lib = load_library()
+        h = _vp()
+        if devices is None:
+            rc = self.lib.b200_multi_create(None, 0, ctypes.byref(h))
+        else:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            rc = self.lib.b200_multi_create(arr, len(devices), ctypes.byref(h))
+        if rc != 0:
+            raise B200Error("b200_multi_create failed with %d" % rc)
+        self.h = h
+        self.lib.b200_multi_last_error.restype = ctypes.c_char_p
+        self.n_seq = 0
+
+    @property
+    def size(self):
+        return int(self.lib.b200_multi_size(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B200Error("b200_multi error %d: %s" % (rc, self.lib.b200_multi_last_error(self.h).decode()))
+
+    def load_db(self, residues, offsets, alphabet, shard_targets=False):
+        residues = np.ascontiguousarray(residues, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        self._check(self.lib.b200_multi_db_load(self.h, _p(residues), _p(offsets), _u64(len(offsets) - 1), int(alphabet), 1 if shard_targets else 0))
+        self.n_seq = len(offsets) - 1
+        self._db_len = np.diff(offsets.astype(np.int64))
+
+    def db_lengths(self):
+        return self._db_len
+
+    def ungapped_scan(self, queries, min_score_excl=15, max_hits=300):
+        cq = _cqueries(queries)
+        nq = len(queries)
+        hits = np.zeros((nq, max_hits), HIT_DTYPE)
+        n_hits = np.zeros(nq, np.uint32)
+        self._check(self.lib.b200_multi_ungapped_scan(self.h, cq, nq, int(min_score_excl), ctypes.c_uint32(max_hits), _p(hits), _p(n_hits)))
+        return hits, n_hits

@@ -17,7 +17,7 @@ def _declared(header):
 
 def test_library_exports_every_declared_symbol(built_lib):
     lib = ctypes.CDLL(built_lib)
-    names = _declared("b200_align.h") + _declared("b200_host.h") + _declared("b200_alignment.h") + _declared("b200_db.h") + _declared("b200_gpuserver.h")
+    names = _declared("b200_align.h") + _declared("b200_host.h") + _declared("b200_alignment.h") + _declared("b200_db.h") + _declared("b200_gpuserver.h") + _declared("b200_multi.h")
     assert len(names) >= 53
     for n in names:
         assert hasattr(lib, n), "missing export: " + n
