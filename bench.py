@@ -58,28 +58,50 @@ def make_scan_workload(rank, db_seqs, queries_per_step, n_steps_distinct):
 
 
 def make_sw_workload(n_queries, targets_per_query):
-    """config[2] in miniature: (query,target) pairs, lengths log-uniform in [50,2000], half random, half homologs at
-    20-90 % identity, so byte and word modes are both exercised."""
+    """config[2]: (query,target) pairs -- prefilter-hit lists of n_queries queries --, lengths log-uniform in [50,2000], half of
+    every list random sequences, half homologs of the query at 20-90 % identity with indels, so byte and word modes are both
+    exercised.  n_queries x targets_per_query = the number of pairs (BASELINE: 1 M)."""
     from mmseqs2_b200 import synth
     mat, pb = load_matrix()
     bg = synth.background(pb)
+    cdf = np.cumsum(bg)
     rng = np.random.default_rng(77)
-    queries, targets, pairs = [], [], []
+    n_hom = targets_per_query // 2
+    n_rand = targets_per_query - n_hom
+    # one pool of random targets shared by all lists (drawn without replacement per query); homologs generated per query
+    pool_n = max(4 * n_rand, 4096)
+    pool_len = np.exp(rng.uniform(np.log(50), np.log(2000), pool_n)).astype(np.int64)
+    chunks = [np.minimum(np.searchsorted(cdf, rng.random(int(pool_len.sum())), side="right"), 19).astype(np.uint8)]
+    lens = [pool_len]
+    queries, pairs = [], []
+    n_targets = pool_n
+    gen = None
+    try:   # homolog generation on the GPU when there is one (data plumbing; the numpy path produces the same kind of data, slower)
+        import torch
+        if torch.cuda.is_available():
+            gen = torch.Generator(device="cuda")
+            gen.manual_seed(77)
+    except Exception:
+        gen = None
     for qi in range(n_queries):
         L = int(np.exp(rng.uniform(np.log(50), np.log(2000))))
-        q = synth.random_seqs(rng, 1, bg, mean=L, sigma=0, lo=L, hi=L, normal=True)[0]
+        q = np.minimum(np.searchsorted(cdf, rng.random(L), side="right"), 19).astype(np.uint8)
         queries.append(q)
-        for k in range(targets_per_query):
-            if k % 2 == 0:
-                T = int(np.exp(rng.uniform(np.log(50), np.log(2000))))
-                t = synth.random_seqs(rng, 1, bg, mean=T, sigma=0, lo=T, hi=T, normal=True)[0]
+        ids = np.empty(targets_per_query, np.int64)
+        ids[:n_rand] = rng.choice(pool_n, n_rand, replace=False)
+        if n_hom:
+            if gen is not None:
+                hd, hl = synth.mutate_many_torch(gen, q, n_hom, 0.2, 0.9, 0.02)
+                hd, hl = hd.cpu().numpy(), hl.cpu().numpy()
             else:
-                ident = rng.uniform(0.2, 0.9)
-                t = synth.mutate(rng, q, bg, subst=1.0 - ident, indel=0.02)
-            pairs.append((qi, len(targets)))
-            targets.append(t)
-    td, to = synth.pack(targets)
-    return queries, td, to, np.array(pairs, np.uint32)
+                hd, hl = synth.mutate_many(rng, q, n_hom, bg, 0.2, 0.9, 0.02)
+            chunks.append(hd); lens.append(hl)
+            ids[n_rand:] = n_targets + np.arange(n_hom)
+            n_targets += n_hom
+        pairs.append(np.stack([np.full(targets_per_query, qi, np.int64), ids], 1))
+    to = np.zeros(n_targets + 1, np.uint64)
+    to[1:] = np.cumsum(np.concatenate(lens))
+    return queries, np.concatenate(chunks), to, np.concatenate(pairs).astype(np.uint32)
 
 
 class ClockSampler:
@@ -376,8 +398,11 @@ def main():
     ap.add_argument("--queries-per-step", type=int, default=16)
     ap.add_argument("--max-hits", type=int, default=300)
     ap.add_argument("--no-secondary", action="store_true")
-    ap.add_argument("--sw-queries", type=int, default=512)
-    ap.add_argument("--sw-targets", type=int, default=256)
+    ap.add_argument("--sw-queries", type=int, default=1024)     # x --sw-targets = 1 M pairs: BASELINE config[2]
+    ap.add_argument("--sw-targets", type=int, default=1024)
+    ap.add_argument("--no-libmarv", action="store_true", help="skip the reference's own GPU scorer (baseline/_ref) on the same DB")
+    ap.add_argument("--search-wallclock", type=int, default=0, metavar="Q",
+                    help="also run `mmseqs search` through the patched reference host vs the AVX2 build on Q queries (integration/search_wallclock.py)")
     ap.add_argument("--nucl-reads", type=int, default=200000)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the scan's cpu_baseline leg")
@@ -688,6 +713,64 @@ def main():
             except Exception as e:  # pragma: no cover
                 line.setdefault("secondary", {})["sw_rescoring"] = {"error": repr(e)}
 
+        # ---- secondary: the reference's own GPU scorer (libmarv, built in place by baseline/Makefile) on the same DB and queries ----
+        if not args.no_secondary and not args.no_libmarv and world == 1:
+            try:
+                from baseline import marv
+                if marv.available():
+                    # our context goes first: both libraries want the whole GPU
+                    mq = batch_seqs[0] + batch_seqs[1]
+                    mp = [p.profile for p in batches[0] + batches[1]]
+                    tb, _ = marv.time_tables(res, off, mq, mp, tables=("as_shipped", "sm90_dpx"), max_seqs=args.max_hits)
+                    line.setdefault("secondary", {})["libmarv"] = {
+                        "what": "Marv::scan of the reference (lib/libmarv compiled for sm_100, one call per query as ungappedprefilter.cpp:207 does) "
+                                "on the same %d-sequence DB and the same %d queries; as_shipped = the kernel table libmarv selects on cc 10.0 "
+                                "(its sm_89 half2 table), sm90_dpx = its H100 short2/DPX table installed through setCustomKernelConfig_Gapless" % (args.db_seqs, len(mq)),
+                        "GCUPS": tb, "b200_e2e_GCUPS": e2e_value,
+                        "b200_over_libmarv_best": e2e_value / max(v["gcups_wall"] for v in tb.values())}
+                else:
+                    line.setdefault("secondary", {})["libmarv"] = {"unavailable": "baseline/_ref/libmarv_harness.so not built (make -C baseline)"}
+            except Exception as e:  # pragma: no cover
+                line.setdefault("secondary", {})["libmarv"] = {"error": repr(e)}
+
+        # ---- secondary: A1, the per-diagonal scorer of the k-mer prefilter, batched over queries (b200_diag_score_batch) -----------
+        if not args.no_secondary and world == 1:
+            try:
+                rng = np.random.default_rng(6)
+                ctx.load_db(res, off, 21)
+                nqd, per_q = 64, 50000
+                dqs = (queries * ((nqd + len(queries) - 1) // len(queries)))[:nqd]
+                dprofs = [sm.diag_query(q, sm.comp_bias(q)) for q in dqs]
+                lens = np.diff(np.asarray(off, np.int64))
+                lists = []
+                cells = 0
+                for q in dqs:
+                    ids = rng.integers(0, len(lens), per_q).astype(np.uint32)
+                    dg = rng.integers(-(lens[ids] - 1), len(q), per_q)                # a diagonal that meets the rectangle
+                    L = np.where(dg >= 0, np.minimum(lens[ids], len(q) - dg), np.minimum(lens[ids] + dg, len(q)))
+                    cells += int(L.sum())
+                    lists.append((ids, (dg & 0xffff).astype(np.uint16)))
+                ctx.diag_score_batch(dprofs[:4], lists[:4])
+                t0 = time.perf_counter()
+                ctx.diag_score_batch(dprofs, lists)
+                ddt = time.perf_counter() - t0
+                dk_ms = ctx.last_kernel_ms
+                t0 = time.perf_counter()
+                for i in range(8):
+                    ctx.diag_score(dprofs[i], lists[i][0], lists[i][1])
+                one_dt = (time.perf_counter() - t0) / 8
+                nh = nqd * per_q
+                dbytes = cells + nh * (7 + 1)       # diagonal length + 7 B hit record in + 1 B out per hit
+                line.setdefault("secondary", {})["diag_score"] = {
+                    "workload": "per-diagonal scorer (A1): %d queries x %d (target, diagonal) hits on the %d-sequence DB, one batched call" % (nqd, per_q, args.db_seqs),
+                    "hits_per_s": nh / (dk_ms / 1e3), "kernel_ms": dk_ms, "cells": cells,
+                    "e2e": {"hits_per_s": nh / ddt, "ms": ddt * 1e3, "per_query_calls_hits_per_s": per_q / one_dt},
+                    "roofline": {"bound": "hbm", "achieved": dbytes / 1e9 / (dk_ms / 1e3), "unit": "GB/s", "peak": roof["hbm"]["peak_gbs"],
+                                 "frac": dbytes / 1e9 / (dk_ms / 1e3) / roof["hbm"]["peak_gbs"],
+                                 "note": "random gathers of ~%d-residue diagonals: latency bound; sectors fetched exceed the algorithmic bytes" % (cells // nh)}}
+            except Exception as e:  # pragma: no cover
+                line.setdefault("secondary", {})["diag_score"] = {"error": repr(e)}
+
         # ---- secondary: nucleotide gapped aligner (config[4] shape in miniature: 150-bp reads vs genome pieces) ------------
         if not args.no_secondary and world == 1:
             try:
@@ -709,6 +792,11 @@ def main():
                         "aligned_residues_per_s": float((nout["qend"] - nout["qstart"] + 1).sum()) / ndt,
                         "kernel": "nucl_align_kernel", "kernel_ms": nk_ms, "value": len(reads) / (nk_ms / 1e3), "unit": "alignments/s",
                         "mean_score": float(nout["score"].mean())}
+                # SURVEY 8(d) for A7: HBM/latency bound; algorithmic bytes = 2 * (150 + band 64) residues + 32 B result per read
+                nbytes = len(reads) * (2 * (150 + 64) + 32)
+                nsec["roofline"] = {"bound": "hbm", "achieved": nbytes / 1e9 / (nk_ms / 1e3), "unit": "GB/s", "peak": roof["hbm"]["peak_gbs"],
+                                    "frac": nbytes / 1e9 / (nk_ms / 1e3) / roof["hbm"]["peak_gbs"], "bytes_per_read": 2 * (150 + 64) + 32,
+                                    "note": "tiny DPs (150 x <=214 cells in band 64): the kernel is occupancy/latency bound, not bandwidth bound"}
                 if not args.no_cpu:
                     from oracle.pyoracle import Ref
                     if Ref.available():
@@ -730,6 +818,15 @@ def main():
                 line["cpu_baseline"] = cpu_reference_gcups(batch_seqs, res, off, args.cpu_budget, gpu_dense, gpu_hits, 15, args.max_hits)
             except Exception as e:  # pragma: no cover
                 line["cpu_baseline"] = {"error": repr(e)}
+        if args.search_wallclock > 0 and world == 1:
+            try:
+                outp = os.path.join(ROOT, "gpurun_out", "search_wallclock_bench.json")
+                subprocess.run([sys.executable, os.path.join(ROOT, "integration", "search_wallclock.py"), "--db-seqs", str(args.db_seqs),
+                                "--queries", str(args.search_wallclock), "--cpu-queries", str(max(16, args.search_wallclock // 8)), "--out", outp],
+                               check=True, capture_output=True, timeout=3000)
+                line["search_wallclock"] = json.load(open(outp))
+            except Exception as e:  # pragma: no cover
+                line["search_wallclock"] = {"error": repr(e)}
         print(json.dumps(line))
     for j in jobs:
         j.close()

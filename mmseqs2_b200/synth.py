@@ -49,6 +49,57 @@ def mutate(rng, seq, bg, subst=0.3, indel=0.02):
     return res.astype(np.uint8)
 
 
+def mutate_many(rng, seq, n, bg, ident_lo=0.2, ident_hi=0.9, indel=0.02):
+    """n mutated copies of seq at identities uniform in [ident_lo, ident_hi], fully vectorised: substitutions by a mask over an
+    [n][L] tile, deletions (indel/2 per residue) and 3-residue insertions (indel/6 per residue) by repeating every cell 0, 1 or 4
+    times.  -> (residues concatenated, lengths[n]).  For the 1 M-pair SW workload."""
+    seq = np.asarray(seq, np.uint8)
+    L = len(seq)
+    cdf = np.cumsum(bg)
+    rows = np.tile(seq, (n, 1))
+    subst = 1.0 - rng.uniform(ident_lo, ident_hi, n)
+    mask = rng.random((n, L)) < subst[:, None]
+    rows[mask] = np.minimum(np.searchsorted(cdf, rng.random(int(mask.sum())), side="right"), 19).astype(np.uint8)
+    u = rng.random((n, L))
+    counts = np.ones((n, L), np.int64)
+    counts[u < indel / 2] = 0
+    counts[(u >= indel / 2) & (u < indel / 2 + indel / 6)] = 4
+    counts[:, 0] = np.maximum(counts[:, 0], 1)                 # never an empty sequence
+    flat_counts = counts.reshape(-1)
+    data = np.repeat(rows.reshape(-1), flat_counts)
+    # the 2nd..4th copy of a repeated cell is an inserted random residue
+    starts = np.cumsum(flat_counts) - flat_counts
+    within = np.arange(len(data)) - np.repeat(starts, flat_counts)
+    ins = within > 0
+    data[ins] = np.minimum(np.searchsorted(cdf, rng.random(int(ins.sum())), side="right"), 19).astype(np.uint8)
+    return data, counts.sum(1)
+
+
+def mutate_many_torch(gen, seq, n, ident_lo=0.2, ident_hi=0.9, indel=0.02, device="cuda"):
+    """mutate_many on the GPU (synthetic-data plumbing for the 1 M-pair workload: 5e8 residues of homologs take minutes in numpy);
+    substituted / inserted residues are uniform over the 20 letters.  gen: torch.Generator on `device`.  -> (uint8 tensor, lengths)"""
+    import torch
+    q = torch.as_tensor(np.asarray(seq, np.uint8), device=device)
+    L = q.numel()
+    rows = q.repeat(n, 1)
+    subst = 1.0 - (ident_lo + (ident_hi - ident_lo) * torch.rand(n, device=device, generator=gen))
+    mask = torch.rand((n, L), device=device, generator=gen) < subst[:, None]
+    rnd = torch.randint(0, 20, (n, L), device=device, generator=gen, dtype=torch.uint8)
+    rows = torch.where(mask, rnd, rows)
+    u = torch.rand((n, L), device=device, generator=gen)
+    counts = torch.ones((n, L), dtype=torch.int64, device=device)
+    counts[u < indel / 2] = 0
+    counts[(u >= indel / 2) & (u < indel / 2 + indel / 6)] = 4
+    counts[:, 0].clamp_(min=1)
+    flat = counts.reshape(-1)
+    data = torch.repeat_interleave(rows.reshape(-1), flat)
+    starts = torch.cumsum(flat, 0) - flat
+    within = torch.arange(data.numel(), device=device) - torch.repeat_interleave(starts, flat)
+    ins = within > 0
+    data = torch.where(ins, torch.randint(0, 20, (data.numel(),), device=device, generator=gen, dtype=torch.uint8), data)
+    return data, counts.sum(1)
+
+
 def plant_homologs(rng, res, off, queries, bg, frac=0.01, subst=0.3, indel=0.02):
     """overwrite a window of ~frac of the targets with a mutated copy of a random query segment (in place)"""
     n = len(off) - 1
