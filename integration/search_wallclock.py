@@ -77,7 +77,8 @@ def read_db(path):
 
 
 def md5(path):
-    return hashlib.md5(open(path, "rb").read()).hexdigest()
+    """md5 of the sorted lines: the alignment DB is written by several threads, so convertalis emits queries in varying order"""
+    return hashlib.md5(b"".join(sorted(open(path, "rb").read().splitlines(True)))).hexdigest()
 
 
 def step_times(log):
@@ -104,7 +105,7 @@ def main():
     ap.add_argument("--db-seqs", type=int, default=1000000)
     ap.add_argument("--queries", type=int, default=1024)
     ap.add_argument("--cpu-queries", type=int, default=256, help="CPU arm runs on the first N queries (0 = skip the CPU arm)")
-    ap.add_argument("--threads", type=int, default=len(os.sched_getaffinity(0)))
+    ap.add_argument("--threads", type=int, default=0, help="0 = what the box really offers: min(affinity mask, cgroup cpu.max quota)")
     ap.add_argument("--work", default="/tmp/b200_search")
     ap.add_argument("--examples", default=None, help="directory with QUERY.fasta and DB.fasta (reference examples/)")
     ap.add_argument("--no-gpu", action="store_true")
@@ -113,6 +114,9 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "search_wallclock.json"))
     args = ap.parse_args()
 
+    if args.threads <= 0:
+        import bench as _b
+        args.threads = _b.cpu_info()["threads_used"]
     cpu_bin = os.path.join(HERE, "_build", "mmseqs_avx2")
     gpu_bin = os.path.join(HERE, "_build", "mmseqs_b200")
     W = args.work

@@ -102,8 +102,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 #ifndef B200_SCAN_MINB
 #define B200_SCAN_MINB 3
 #endif
+#ifndef B200_SCAN_K3
+#define B200_SCAN_K3 24      // classes up to this K are compiled for B200_SCAN_MINB CTAs per SM
+#endif
 template <int G, int K, bool TILED>
-__global__ void __launch_bounds__(256, TILED ? 1 : (K <= 12 ? 5 : (K <= 24 ? B200_SCAN_MINB : 1)))
+__global__ void __launch_bounds__(256, TILED ? 1 : (K <= 12 ? 5 : (K <= B200_SCAN_K3 ? B200_SCAN_MINB : 1)))
 ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict__ qd, const uint8_t *__restrict__ db,
                      const uint64_t *__restrict__ off, const int32_t *__restrict__ len,
                      const uint32_t *__restrict__ order, uint32_t n_seq, int A, uint8_t *__restrict__ out, uint32_t n_queries,
@@ -242,9 +245,11 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
                     if (g == 0) carry = TILED ? bin[u >> 1] : 0u;
                     const uint32_t *prow = Pp + a1 * ROW_W;
                     const uint4 *p = reinterpret_cast<const uint4 *>(prow) + g;
+#ifndef B200_SCAN_NO_PRELOAD
                     uint4 x[C > 0 ? C : 1];
 #pragma unroll
                     for (int c = 0; c < C; c++) x[c] = p[c * G];
+#endif
                     if (T) {
                         const uint2 xt = reinterpret_cast<const uint2 *>(prow + tail_off)[g];
                         S[4 * C + 1] = __viaddmin_s16x2_relu(S[4 * C + 0], xt.y, cst);
@@ -252,10 +257,15 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
                     }
 #pragma unroll
                     for (int c = C - 1; c >= 0; c--) {
-                        S[4 * c + 3] = __viaddmin_s16x2_relu(S[4 * c + 2], x[c].w, cst);
-                        S[4 * c + 2] = __viaddmin_s16x2_relu(S[4 * c + 1], x[c].z, cst);
-                        S[4 * c + 1] = __viaddmin_s16x2_relu(S[4 * c + 0], x[c].y, cst);
-                        S[4 * c + 0] = __viaddmin_s16x2_relu(c > 0 ? S[4 * c - 1] : carry, x[c].x, cst);
+#ifdef B200_SCAN_NO_PRELOAD
+                        const uint4 xc = p[c * G];
+#else
+                        const uint4 xc = x[c];
+#endif
+                        S[4 * c + 3] = __viaddmin_s16x2_relu(S[4 * c + 2], xc.w, cst);
+                        S[4 * c + 2] = __viaddmin_s16x2_relu(S[4 * c + 1], xc.z, cst);
+                        S[4 * c + 1] = __viaddmin_s16x2_relu(S[4 * c + 0], xc.y, cst);
+                        S[4 * c + 0] = __viaddmin_s16x2_relu(c > 0 ? S[4 * c - 1] : carry, xc.x, cst);
                     }
 #pragma unroll
                     for (int r = 0; r < K; r += 2) best = __vimax3_s16x2(best, S[r], S[r + 1]);
