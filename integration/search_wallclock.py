@@ -111,6 +111,7 @@ def main():
     ap.add_argument("--no-gpu", action="store_true")
     ap.add_argument("--backtrace", action="store_true", help="search -a")
     ap.add_argument("--alignment-mode", type=int, default=None)
+    ap.add_argument("--target-queries", type=int, default=100000, help="job size the two arms are extrapolated to (north_star: 100k x 1M)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "search_wallclock.json"))
     args = ap.parse_args()
 
@@ -203,6 +204,19 @@ def main():
             if ncpu == nq_total:
                 out["parity"]["m8_md5_equal"] = out["cpu"]["m8_md5"] == out["b200"]["m8_md5"]
             out["speedup_search_wallclock"] = out["cpu"]["wall_s_scaled_to_all_queries"] / out["b200"]["wall_s"]
+            if ncpu < nq_total and args.target_queries > 0:
+                # Both arms are (fixed cost) + (per-query cost) x queries: start-up, DB load and index reading do not grow with the
+                # query count, the ungapped prefilter and the alignments do.  The B200 arm is measured at two sizes (the CPU arm's
+                # subsample and all queries), which gives its fixed and per-query parts; the CPU arm's fixed part is taken as zero
+                # (the assumption that favours the CPU).  Extrapolation to the north_star job size, stated as such.
+                out["b200_sub"], _, _ = search(gpu_bin, QC, "b200_sub", ["--gpu", "1"])
+                per_q = (out["b200"]["wall_s"] - out["b200_sub"]["wall_s"]) / (nq_total - ncpu)
+                fixed = out["b200"]["wall_s"] - per_q * nq_total
+                cpu_per_q = out["cpu"]["wall_s"] / ncpu
+                tq = args.target_queries
+                out["extrapolation"] = {"target_queries": tq, "b200_fixed_s": fixed, "b200_per_query_s": per_q, "cpu_per_query_s": cpu_per_q,
+                                        "b200_s": fixed + per_q * tq, "cpu_s": cpu_per_q * tq, "speedup": cpu_per_q * tq / (fixed + per_q * tq),
+                                        "note": "linear in queries; CPU fixed cost taken as 0; same box, same thread count for both arms"}
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(out, open(args.out, "w"), indent=1)
     print(json.dumps(out))
