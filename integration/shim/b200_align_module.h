@@ -20,6 +20,7 @@
 
 #include "b200_align.h"
 #include "b200_alignment.h"
+#include "b200_multi.h"
 
 #include "DBReader.h"
 #include "DBWriter.h"
@@ -73,10 +74,12 @@ static inline bool alignOnDevice(DBReader<DBKeyType> *qdbr, DBReader<DBKeyType> 
 
     const int A = m->alphabetSize;
     const unsigned int threads = s.threads > 0 ? s.threads : 1;
-    b200_ctx *ctx = NULL;
+    // every visible device (B200_DEVICE=<id> pins one): target DB replicated, each bucket's queries split across the devices
+    b200_multi *multi = NULL;
     const char *dev = getenv("B200_DEVICE");
-    if (b200_create(dev != NULL ? atoi(dev) : 0, &ctx) != B200_OK) {
-        Debug(Debug::ERROR) << "libb200align: b200_create failed\n";
+    const int oneDev = dev != NULL ? atoi(dev) : 0;
+    if ((dev != NULL ? b200_multi_create(&oneDev, 1, &multi) : b200_multi_create(NULL, 0, &multi)) != B200_OK) {
+        Debug(Debug::ERROR) << "libb200align: b200_multi_create failed\n";
         EXIT(EXIT_FAILURE);
     }
 
@@ -102,9 +105,9 @@ static inline bool alignOnDevice(DBReader<DBKeyType> *qdbr, DBReader<DBKeyType> 
             memcpy(tRes.data() + tOff[i], dbSeq.numSequence, (size_t) dbSeq.L);
         }
     }
-    int rc = b200_db_load(ctx, tRes.data(), tOff.data(), nT, A);
+    int rc = b200_multi_db_load(multi, tRes.data(), tOff.data(), nT, A, /*shard_targets=*/0);
     if (rc != B200_OK) {
-        Debug(Debug::ERROR) << "libb200align: b200_db_load failed: " << b200_last_error(ctx) << "\n";
+        Debug(Debug::ERROR) << "libb200align: b200_db_load failed: " << b200_multi_last_error(multi) << "\n";
         EXIT(EXIT_FAILURE);
     }
     std::vector<uint8_t>().swap(tRes);
@@ -203,13 +206,13 @@ static inline bool alignOnDevice(DBReader<DBKeyType> *qdbr, DBReader<DBKeyType> 
             uint64_t btCap = s.swMode == Matcher::SCORE_COV_SEQID ? (uint64_t) 64 << 20 : 16;
             while (true) {
                 btPool.resize(btCap);
-                rc = b200_align_batch(ctx, mat.data(), m->pBack, A, qRes.data(), qOff.data(), qKeys.data(), (uint32_t) nQ, hOff.data(),
+                rc = b200_multi_align_batch(multi, mat.data(), m->pBack, A, qRes.data(), qOff.data(), qKeys.data(), (uint32_t) nQ, hOff.data(),
                                       hTargets.data(), tKeys.data(), &p, &ev, results.data(), nResults.data(), btPool.data(), btCap, &nAln);
                 if (rc == B200_ERR_RANGE && btCap < ((uint64_t) 1 << 36)) { btCap *= 4; continue; }   // backtrace pool too small
                 break;
             }
             if (rc != B200_OK) {
-                Debug(Debug::ERROR) << "libb200align: b200_align_batch failed: " << b200_last_error(ctx) << "\n";
+                Debug(Debug::ERROR) << "libb200align: b200_align_batch failed: " << b200_multi_last_error(multi) << "\n";
                 EXIT(EXIT_FAILURE);
             }
         }
@@ -246,7 +249,7 @@ static inline bool alignOnDevice(DBReader<DBKeyType> *qdbr, DBReader<DBKeyType> 
         }
         id = end;
     }
-    b200_destroy(ctx);
+    b200_multi_destroy(multi);
     return true;
 }
 

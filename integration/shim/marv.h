@@ -25,6 +25,7 @@
 
 #include "b200_align.h"
 #include "b200_host.h"
+#include "b200_multi.h"
 
 class Marv {
 public:
@@ -52,20 +53,30 @@ public:
     };
 
     Marv(size_t dbEntries, int alphabetSize, int maxSeqLength, size_t maxSeqs, AlignmentType alignmentType = AlignmentType::GAPLESS)
-        : dbEntries(dbEntries), alphabetSize(alphabetSize), maxSeqs(maxSeqs), alignmentType(alignmentType), ctx(NULL),
+        : dbEntries(dbEntries), alphabetSize(alphabetSize), maxSeqs(maxSeqs), alignmentType(alignmentType), multi(NULL), ctx(NULL),
           gapOpen(11), gapExtend(1) {
         (void) maxSeqLength;
+        // Like libmarv, every visible device is used (CUDA_VISIBLE_DEVICES selects them): the DB is cut into per-device slices and
+        // each query is scanned against all slices at once (target-sharded, include/b200_multi.h).  B200_DEVICE=<id> pins one device;
+        // the gapped rescoring mode needs the whole DB next to the scan and also stays on one device.
         const char *dev = getenv("B200_DEVICE");
-        const int rc = b200_create(dev != NULL ? atoi(dev) : 0, &ctx);
+        int rc;
+        if (dev != NULL || alignmentType != GAPLESS) {
+            const int id = dev != NULL ? atoi(dev) : 0;
+            rc = b200_multi_create(&id, 1, &multi);
+        } else {
+            rc = b200_multi_create(NULL, 0, &multi);
+        }
         if (rc != B200_OK) {
-            fprintf(stderr, "libb200align: b200_create failed (%d)\n", rc);
+            fprintf(stderr, "libb200align: b200_multi_create failed (%d)\n", rc);
             exit(EXIT_FAILURE);
         }
+        ctx = b200_multi_ctx(multi, 0);
     }
 
     ~Marv() {
-        if (ctx != NULL) {
-            b200_destroy(ctx);
+        if (multi != NULL) {
+            b200_multi_destroy(multi);
         }
     }
 
@@ -83,8 +94,9 @@ public:
     // Masked residues become X, as the CPU scorer treats them (ungappedprefilter.cpp:401-404).
     void* loadDb(char* data, size_t* offset, int32_t* length, size_t dbByteSize) {
         (void) dbByteSize;
-        const int rc = b200_db_load_padded(ctx, reinterpret_cast<const uint8_t*>(data), offset, length, dbEntries, alphabetSize);
-        check(rc, "loadDb");
+        const int rc = b200_multi_db_load_padded(multi, reinterpret_cast<const uint8_t*>(data), offset, length, dbEntries, alphabetSize,
+                                                 /*shard_targets=*/1);
+        checkMulti(rc, "loadDb");
         return this;
     }
 
@@ -122,8 +134,8 @@ public:
         hits.resize(maxSeqs);
         uint32_t n = 0;
         // libmarv returns the maxSeqs best targets whatever their score; the caller filters by --min-ungapped-score
-        int rc = b200_ungapped_scan(ctx, &q, 1, /*min_score_excl=*/-1, (uint32_t) maxSeqs, hits.data(), &n, NULL);
-        check(rc, "scan");
+        int rc = b200_multi_ungapped_scan(multi, &q, 1, /*min_score_excl=*/-1, (uint32_t) maxSeqs, hits.data(), &n);
+        checkMulti(rc, "scan");
         if (alignmentType == GAPLESS) {
             for (uint32_t i = 0; i < n; i++) {
                 results[i] = Result(hits[i].id, hits[i].score, -1, -1);
@@ -159,6 +171,13 @@ public:
     }
 
 private:
+    void checkMulti(int rc, const char *what) {
+        if (rc != B200_OK) {
+            fprintf(stderr, "libb200align: %s failed (%d): %s\n", what, rc, b200_multi_last_error(multi));
+            exit(EXIT_FAILURE);
+        }
+    }
+
     void check(int rc, const char *what) {
         if (rc != B200_OK) {
             fprintf(stderr, "libb200align: %s failed (%d): %s\n", what, rc, b200_last_error(ctx));
@@ -170,7 +189,8 @@ private:
     int alphabetSize;
     size_t maxSeqs;
     AlignmentType alignmentType;
-    b200_ctx* ctx;
+    b200_multi* multi;
+    b200_ctx* ctx;            // device 0 of the handle (the gapped rescoring runs there)
     int gapOpen, gapExtend;
     std::vector<int16_t> mat;
     std::vector<b200_hit> hits;
