@@ -46,7 +46,8 @@ def test_rescore_diagonal_matches_reference_outputs(ctx):
     for mode in range(5):
         out = ctx.rescore_diagonal(queries, lists, g["asciimat"], mode)
         got = np.stack([out[f] for f in FIELDS], 1).astype(np.int64)
-        assert np.array_equal(got, g["expected"][mode]), (mode, np.nonzero((got != g["expected"][mode]).any(1))[0][:5])
+        exp = g["expected"][mode].astype(np.int64).astype(np.int32).astype(np.int64)   # LocalAlignment::score is unsigned: same 32 bits
+        assert np.array_equal(got, exp), (mode, np.nonzero((got != exp).any(1))[0][:5])
         for k, (qi, ti, dg) in enumerate(hits):
             exp_id = _ident(queries[qi], g["tdata"][to[ti]:to[ti + 1]].tobytes(), out[k]) if mode >= 2 else 0
             assert out["identical"][k] == exp_id, (mode, k)
@@ -84,7 +85,7 @@ def test_rescore_diagonal_random_vs_oracle(ctx, oracle):
         k = 0
         for qi, (ids, dgs) in enumerate(lists):
             for ti, dg in zip(ids, dgs):
-                exp = oracle.rescore_diagonal(queries[qi], targets[int(ti)], int(dg), m, mode)
+                exp = oracle.rescore_diagonal(queries[qi], targets[int(ti)], int(dg), m, mode).astype(np.int32).astype(np.int64)
                 got = np.array([out[f][k] for f in FIELDS], np.int64)
                 assert np.array_equal(got, exp), (mode, qi, int(ti), got, exp)
                 if mode >= 2:
