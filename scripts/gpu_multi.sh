@@ -1,9 +1,24 @@
 #!/bin/bash
-# N-GPU run of the bench through torchrun (NCCL gather of the hit lists)
+# scripts/gpu_multi.sh N -- multi-GPU evidence on an N-GPU box: the multi-device handle's tests, bench at 1..N, optionally the configs[3]/[4] script
 N=${1:-2}
 mkdir -p gpurun_out
-nvidia-smi -L > gpurun_out/gpus.txt
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "exit $?"
-cat gpurun_out/bench_n$N.json | cut -c1-400; tail -3 gpurun_out/bench_n$N.err
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --impl reference --gpus $N --steps 2 --warmup 1 > gpurun_out/bench_ref_n$N.json 2> gpurun_out/bench_ref_n$N.err; echo "exit $?"
-cat gpurun_out/bench_ref_n$N.json | cut -c1-300
+python -m pytest tests/test_multi_device.py -x -q -m gpu 2>&1 | tail -3
+for n in 1 $N; do
+  if [ "$n" = 1 ]; then
+    python bench.py --gpus 1 --steps 10 --warmup 3 --no-secondary --no-cpu > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+  else
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err
+  fi
+  python - <<PY
+import json
+try:
+    d = json.loads(open("gpurun_out/bench_n$n.json").read().strip().splitlines()[-1])
+    print("N=$n value %.0f ms_per_step %.2f e2e %.0f" % (d["value"], d["ms_per_step"], d["e2e"]["value"]))
+except Exception as e:
+    print("N=$n failed", e); print(open("gpurun_out/bench_n$n.err").read()[-1500:])
+PY
+done
+if [ "$2" = configs ]; then
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 scripts/multi_gpu_configs.py $3 2> gpurun_out/configs.err | tail -c 3000
+  tail -5 gpurun_out/configs.err
+fi
