@@ -961,6 +961,25 @@ namespace {
 
 int set_err(b200_ctx *ctx, int code, const char *msg) { return b200_set_err(ctx, code, msg); }
 
+// int16 safety of the packed gapped kernels.  No local alignment (and no intermediate H/E/F value, each the score of some partial
+// path) can exceed either  min(qlen, tlen) * (largest profile entry)  or  the sum over query rows of the row's best entry (every
+// aligned row contributes at most that, unaligned rows nothing).  The second bound is what keeps ordinary long pairs on the packed
+// path: a sequence profile's row maxima average ~11 (its self score), half its largest entry.
+void profile_bounds(const int8_t *pr, int A, int qlen, int &smax, int64_t &qsum) {
+    int m = 1;
+    int64_t sum = 0;
+    for (int j = 0; j < qlen; j++) {
+        int rowmax = 0;
+        for (int a = 0; a < A; a++) rowmax = std::max(rowmax, (int) pr[(size_t) a * qlen + j]);
+        m = std::max(m, rowmax);
+        sum += rowmax;
+    }
+    smax = m; qsum = sum;
+}
+inline bool int16_safe(int smax, int64_t qsum, int qlen, int tlen) {
+    return std::min((int64_t) std::min(qlen, tlen) * smax, qsum) < 32000;
+}
+
 struct ScanCfg { int G, K; };
 // capacity 2*G*K rows, ascending: 32-row steps up to 512 (G=8), 64-row steps up to 1024 (G=16), 128-row steps up to 2048 (G=32)
 #define B200_SCAN_CFGS(X) \
@@ -1721,18 +1740,14 @@ static int sw_score_endpos_locked(b200_ctx *ctx, const std::vector<QueryDesc> &h
     const int A = ctx->alphabet;
     const int nq = (int) h_qd.size();
     std::vector<int> smax(nq, 1);
-    for (int i = 0; i < nq; i++) {
-        int m = 1;
-        const int8_t *pr = queries[i].profile;
-        for (size_t k = 0; k < (size_t) A * queries[i].qlen; k++) m = std::max(m, (int) pr[k]);
-        smax[i] = m;
-    }
+    std::vector<int64_t> qsum(nq, 0);
+    for (size_t q_ = 0; q_ < (size_t) (nq); q_++) profile_bounds(queries[q_].profile, A, queries[q_].qlen, smax[q_], qsum[q_]);
     std::vector<uint8_t> packed(n), rest(n);
     bool any_rest = false, any_packed = false;
     for (uint64_t i = 0; i < n; i++) {
         const int qi = (int) pairs[i].query;
         const int tl = ctx->h_len[pairs[i].target];
-        const bool ok = go >= ge && (int64_t) std::min(queries[qi].qlen, tl) * smax[qi] < 32000;
+        const bool ok = go >= ge && int16_safe(smax[qi], qsum[qi], queries[qi].qlen, tl);
         packed[i] = ok ? 1 : 0; rest[i] = ok ? 0 : 1;
         any_rest |= !ok; any_packed |= ok;
     }
@@ -1791,18 +1806,14 @@ static int sw_startpos_locked(b200_ctx *ctx, const b200_query *queries, const st
     // packed reverse pass where the forward pass was packed too (same int16 safety argument), int32 kernel otherwise
     const int A = ctx->alphabet;
     std::vector<int> smax(h_qd.size(), 1);
-    for (size_t qi = 0; qi < h_qd.size(); qi++) {
-        int m2 = 1;
-        const int8_t *pr = queries[qi].profile;
-        for (size_t k = 0; k < (size_t) A * queries[qi].qlen; k++) m2 = std::max(m2, (int) pr[k]);
-        smax[qi] = m2;
-    }
+    std::vector<int64_t> qsum(h_qd.size(), 0);
+    for (size_t q_ = 0; q_ < (size_t) (h_qd.size()); q_++) profile_bounds(queries[q_].profile, A, queries[q_].qlen, smax[q_], qsum[q_]);
     std::vector<uint8_t> packed(n, 0), rest(n, 0);
     bool any_packed = false, any_rest = false;
     for (uint64_t i = 0; i < n; i++) {
         if (!mask[i]) continue;
         const int qi = (int) pairs[i].query;
-        const bool ok = go >= ge && (int64_t) std::min(queries[qi].qlen, ctx->h_len[pairs[i].target]) * smax[qi] < 32000;
+        const bool ok = go >= ge && int16_safe(smax[qi], qsum[qi], queries[qi].qlen, ctx->h_len[pairs[i].target]);
         packed[i] = ok; rest[i] = !ok;
         any_packed |= ok; any_rest |= !ok;
     }
@@ -2121,12 +2132,8 @@ int b200_sw_score_job_create(b200_ctx *ctx, const b200_query *queries, int nq, c
     const int A = ctx->alphabet;
     // int16 safety: a local alignment cannot score more than min(qlen,tlen) * (largest profile entry)
     std::vector<int> smax(nq, 1);
-    for (int i = 0; i < nq; i++) {
-        int m = 1;
-        const int8_t *pr = queries[i].profile;
-        for (size_t k = 0; k < (size_t) A * queries[i].qlen; k++) m = std::max(m, (int) pr[k]);
-        smax[i] = m;
-    }
+    std::vector<int64_t> qsum(nq, 0);
+    for (size_t q_ = 0; q_ < (size_t) (nq); q_++) profile_bounds(queries[q_].profile, A, queries[q_].qlen, smax[q_], qsum[q_]);
     b200_job *job = new b200_job();
     job->ctx = ctx; job->kind = 3; job->go = go; job->ge = ge; job->n_pairs = n; job->nq = nq;
     const int klass[2] = {1, 0};  // 1: packed int16x2 kernel (any rows-per-lane flavour), 0: int32 fallback
@@ -2140,7 +2147,7 @@ int b200_sw_score_job_create(b200_ctx *ctx, const b200_query *queries, int nq, c
         for (uint64_t i = 0; i < n; i++) {
             const int qi = (int) pairs[i].query;
             const int tl = ctx->h_len[pairs[i].target];
-            const bool packed_ok = go >= ge && (int64_t) std::min(queries[qi].qlen, tl) * smax[qi] < 32000;
+            const bool packed_ok = go >= ge && int16_safe(smax[qi], qsum[qi], queries[qi].qlen, tl);
             const int k = packed_ok ? 1 : 0;
             mask[i] = (k == klass[c]) ? 1 : 0;
             any |= mask[i] != 0;
@@ -2240,17 +2247,13 @@ int b200_sw_score(b200_ctx *ctx, const b200_query *queries, int nq, const b200_p
     if (rc != B200_OK) return rc;
     const int A = ctx->alphabet;
     std::vector<int> smax(nq, 1);
-    for (int i = 0; i < nq; i++) {
-        int m = 1;
-        const int8_t *pr = queries[i].profile;
-        for (size_t k = 0; k < (size_t) A * queries[i].qlen; k++) m = std::max(m, (int) pr[k]);
-        smax[i] = m;
-    }
+    std::vector<int64_t> qsum(nq, 0);
+    for (size_t q_ = 0; q_ < (size_t) (nq); q_++) profile_bounds(queries[q_].profile, A, queries[q_].qlen, smax[q_], qsum[q_]);
     std::vector<uint8_t> packed(n), rest(n);
     bool any_rest = false, any_packed = false;
     for (uint64_t i = 0; i < n; i++) {
         const int qi = (int) pairs[i].query;
-        const bool ok = go >= ge && (int64_t) std::min(queries[qi].qlen, ctx->h_len[pairs[i].target]) * smax[qi] < 32000;
+        const bool ok = go >= ge && int16_safe(smax[qi], qsum[qi], queries[qi].qlen, ctx->h_len[pairs[i].target]);
         packed[i] = ok ? 1 : 0; rest[i] = ok ? 0 : 1;
         any_rest |= !ok; any_packed |= ok;
     }
@@ -2287,17 +2290,13 @@ int b200_sw_endpos(b200_ctx *ctx, const b200_query *queries, int nq, const b200_
     if (rc != B200_OK) return rc;
     const int A = ctx->alphabet;
     std::vector<int> smax(nq, 1);
-    for (int i = 0; i < nq; i++) {
-        int m = 1;
-        const int8_t *pr = queries[i].profile;
-        for (size_t k = 0; k < (size_t) A * queries[i].qlen; k++) m = std::max(m, (int) pr[k]);
-        smax[i] = m;
-    }
+    std::vector<int64_t> qsum(nq, 0);
+    for (size_t q_ = 0; q_ < (size_t) (nq); q_++) profile_bounds(queries[q_].profile, A, queries[q_].qlen, smax[q_], qsum[q_]);
     std::vector<uint8_t> need(n, 0), rest(n, 0);
     bool any_rest = false, any_need = false;
     for (uint64_t i = 0; i < n; i++) {
         const int qi = (int) pairs[i].query;
-        const bool ok = go >= ge && (int64_t) std::min(queries[qi].qlen, ctx->h_len[pairs[i].target]) * smax[qi] < 32000;
+        const bool ok = go >= ge && int16_safe(smax[qi], qsum[qi], queries[qi].qlen, ctx->h_len[pairs[i].target]);
         if (scores[i] < 0) return set_err(ctx, B200_ERR_ARG, "sw_endpos: negative score");
         if (ok) { need[i] = scores[i] > 0 ? 1 : 0; any_need |= need[i] != 0; }
         else { rest[i] = 1; any_rest = true; }

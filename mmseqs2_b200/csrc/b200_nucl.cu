@@ -15,6 +15,7 @@
 #include "b200_internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -270,8 +271,10 @@ __device__ void seed_segment(const int8_t *smat, const uint8_t *s1, const uint8_
     start = maxStart; end = maxEnd; score = maxScore;
 }
 
-template <bool SMEM>
-__global__ void __launch_bounds__(NUCL_WARPS * 32)
+// MINB = resident CTAs per SM the kernel is compiled for (register cap 128 / 80 / 64): the kernel is latency bound (one short
+// dependent chain per anti-diagonal), so more resident warps can pay for a few spilled registers; B200_NUCL_MINB picks at run time.
+template <bool SMEM, int MINB>
+__global__ void __launch_bounds__(NUCL_WARPS * 32, MINB)
 nucl_align_kernel(const NuclTask *__restrict__ tasks, unsigned n_tasks, const uint8_t *__restrict__ qres,
                   const uint64_t *__restrict__ qoff, const uint8_t *__restrict__ db, const uint64_t *__restrict__ off,
                   const int32_t *__restrict__ len, int gapo, int gape, int zdrop, int w, uint8_t *__restrict__ scratch,
@@ -417,10 +420,14 @@ int b200_nucl_align(b200_ctx *ctx, const uint8_t *query_residues, const uint64_t
     const size_t smem_need = round_up(mem_bytes + h_bytes, 16) * NUCL_WARPS;
     const bool use_smem = smem_need <= 96 * 1024;
     int per_sm = 0;
-    if (use_smem) {
-        CU_TRY(ctx, cudaFuncSetAttribute(nucl_align_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_need));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nucl_align_kernel<true>, NUCL_WARPS * 32, smem_need) != cudaSuccess) per_sm = 1;
-    } else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nucl_align_kernel<false>, NUCL_WARPS * 32, 0) != cudaSuccess) per_sm = 1;
+    static const int minb = [] { const char *e = getenv("B200_NUCL_MINB"); const int v = e ? atoi(e) : 2; return v >= 4 ? 4 : (v == 3 ? 3 : 2); }();
+#define NUCL_DISPATCH(EXPR_TRUE, EXPR_FALSE) \
+    do { if (use_smem) { if (minb == 4) { EXPR_TRUE(4); } else if (minb == 3) { EXPR_TRUE(3); } else { EXPR_TRUE(2); } } \
+         else { if (minb == 4) { EXPR_FALSE(4); } else if (minb == 3) { EXPR_FALSE(3); } else { EXPR_FALSE(2); } } } while (0)
+#define NUCL_ATTR_T(M) do { cudaFuncSetAttribute(nucl_align_kernel<true, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_need); \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nucl_align_kernel<true, M>, NUCL_WARPS * 32, smem_need) != cudaSuccess) per_sm = 1; } while (0)
+#define NUCL_ATTR_F(M) do { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nucl_align_kernel<false, M>, NUCL_WARPS * 32, 0) != cudaSuccess) per_sm = 1; } while (0)
+    NUCL_DISPATCH(NUCL_ATTR_T, NUCL_ATTR_F);
     per_sm = std::max(1, per_sm);
     const unsigned grid = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) ctx->sm_count * per_sm, (n + NUCL_WARPS - 1) / NUCL_WARPS));
     uint64_t pool_cap = 0;   // worst case: every alignment fills its slot; what comes back over PCIe is only what was used
@@ -442,16 +449,12 @@ int b200_nucl_align(b200_ctx *ctx, const uint8_t *query_residues, const uint64_t
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_qoff.p, query_offsets, sizeof(uint64_t) * ((size_t) n_queries + 1), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[14], ctx->stream);
     if (e == cudaSuccess) {
-        if (use_smem)
-            nucl_align_kernel<true><<<grid, NUCL_WARPS * 32, smem_need, ctx->stream>>>(
-                d_tasks.as<NuclTask>(), (unsigned) n, d_q.as<uint8_t>(), d_qoff.as<uint64_t>(), ctx->d_res, ctx->d_off, ctx->d_len, gap_open,
-                gap_extend, zdrop, w, d_scratch.as<uint8_t>(), stride, mem_bytes, h_bytes, poff_bytes, pm_bytes, ctx->counter.as<unsigned>(),
-                d_out.as<int32_t>(), d_cig.as<uint32_t>(), d_used.as<unsigned long long>(), w + 8);
-        else
-            nucl_align_kernel<false><<<grid, NUCL_WARPS * 32, 0, ctx->stream>>>(
-                d_tasks.as<NuclTask>(), (unsigned) n, d_q.as<uint8_t>(), d_qoff.as<uint64_t>(), ctx->d_res, ctx->d_off, ctx->d_len, gap_open,
-                gap_extend, zdrop, w, d_scratch.as<uint8_t>(), stride, mem_bytes, h_bytes, poff_bytes, pm_bytes, ctx->counter.as<unsigned>(),
-                d_out.as<int32_t>(), d_cig.as<uint32_t>(), d_used.as<unsigned long long>(), w + 8);
+#define NUCL_ARGS d_tasks.as<NuclTask>(), (unsigned) n, d_q.as<uint8_t>(), d_qoff.as<uint64_t>(), ctx->d_res, ctx->d_off, ctx->d_len, gap_open, \
+                gap_extend, zdrop, w, d_scratch.as<uint8_t>(), stride, mem_bytes, h_bytes, poff_bytes, pm_bytes, ctx->counter.as<unsigned>(), \
+                d_out.as<int32_t>(), d_cig.as<uint32_t>(), d_used.as<unsigned long long>(), w + 8
+#define NUCL_LAUNCH_T(M) nucl_align_kernel<true, M><<<grid, NUCL_WARPS * 32, smem_need, ctx->stream>>>(NUCL_ARGS)
+#define NUCL_LAUNCH_F(M) nucl_align_kernel<false, M><<<grid, NUCL_WARPS * 32, 0, ctx->stream>>>(NUCL_ARGS)
+        NUCL_DISPATCH(NUCL_LAUNCH_T, NUCL_LAUNCH_F);
         ctx->launches++;
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev[15], ctx->stream);
