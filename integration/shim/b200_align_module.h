@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -74,6 +75,9 @@ static inline bool alignOnDevice(DBReader<DBKeyType> *qdbr, DBReader<DBKeyType> 
 
     const int A = m->alphabetSize;
     const unsigned int threads = s.threads > 0 ? s.threads : 1;
+    typedef std::chrono::steady_clock Clock;
+    const Clock::time_point tStart = Clock::now();
+    auto since = [](Clock::time_point a) { return std::chrono::duration<double>(Clock::now() - a).count(); };
     // every visible device (B200_DEVICE=<id> pins one): target DB replicated, each bucket's queries split across the devices
     b200_multi *multi = NULL;
     const char *dev = getenv("B200_DEVICE");
@@ -83,6 +87,7 @@ static inline bool alignOnDevice(DBReader<DBKeyType> *qdbr, DBReader<DBKeyType> 
         EXIT(EXIT_FAILURE);
     }
 
+    const double tCreate = since(tStart);
     // ---- target DB -> numeric residues in HBM (DB-local id == DBReader id) ------------------------------------------------
     const size_t nT = tdbr->getSize();
     std::vector<uint64_t> tOff(nT + 1, 0);
@@ -105,12 +110,15 @@ static inline bool alignOnDevice(DBReader<DBKeyType> *qdbr, DBReader<DBKeyType> 
             memcpy(tRes.data() + tOff[i], dbSeq.numSequence, (size_t) dbSeq.L);
         }
     }
+    const double tMap = since(tStart) - tCreate;
     int rc = b200_multi_db_load(multi, tRes.data(), tOff.data(), nT, A, /*shard_targets=*/0);
     if (rc != B200_OK) {
         Debug(Debug::ERROR) << "libb200align: b200_db_load failed: " << b200_multi_last_error(multi) << "\n";
         EXIT(EXIT_FAILURE);
     }
     std::vector<uint8_t>().swap(tRes);
+    const double tLoad = since(tStart) - tCreate - tMap;
+    double tParse = 0, tDevice = 0, tWrite = 0;
 
     std::vector<int16_t> mat((size_t) A * A);
     for (int i = 0; i < A; i++) {
@@ -147,6 +155,7 @@ static inline bool alignOnDevice(DBReader<DBKeyType> *qdbr, DBReader<DBKeyType> 
             end++;
         }
         const size_t nQ = end - id;
+        const Clock::time_point tb0 = Clock::now();
         perQueryHits.assign(nQ, std::vector<uint32_t>());
         perQuerySeq.assign(nQ, std::vector<uint8_t>());
         qKeys.resize(nQ);
@@ -202,6 +211,8 @@ static inline bool alignOnDevice(DBReader<DBKeyType> *qdbr, DBReader<DBKeyType> 
         results.resize(nHits + 1);
         nResults.assign(nQ, 0);
         uint64_t nAln = 0;
+        tParse += since(tb0);
+        const Clock::time_point tb1 = Clock::now();
         if (nHits > 0) {
             uint64_t btCap = s.swMode == Matcher::SCORE_COV_SEQID ? (uint64_t) 64 << 20 : 16;
             while (true) {
@@ -217,6 +228,8 @@ static inline bool alignOnDevice(DBReader<DBKeyType> *qdbr, DBReader<DBKeyType> 
             }
         }
         alignmentsNum += nAln;
+        tDevice += since(tb1);
+        const Clock::time_point tb2 = Clock::now();
         // ---- records: Matcher::resultToBuffer on the reference's own result_t ---------------------------------------------
 #pragma omp parallel num_threads(threads)
         {
@@ -247,8 +260,11 @@ static inline bool alignOnDevice(DBReader<DBKeyType> *qdbr, DBReader<DBKeyType> 
 #pragma omp atomic
             totalPassedNum += passed;
         }
+        tWrite += since(tb2);
         id = end;
     }
+    Debug(Debug::INFO) << "libb200align align module: context " << tCreate << " s, target DB mapping " << tMap << " s, upload " << tLoad
+                       << " s, prefilter lists + queries " << tParse << " s, b200_align_batch " << tDevice << " s, records " << tWrite << " s\n";
     b200_multi_destroy(multi);
     return true;
 }

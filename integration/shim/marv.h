@@ -20,6 +20,7 @@
 #include <stdio.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -56,6 +57,7 @@ public:
         : dbEntries(dbEntries), alphabetSize(alphabetSize), maxSeqs(maxSeqs), alignmentType(alignmentType), multi(NULL), ctx(NULL),
           gapOpen(11), gapExtend(1) {
         (void) maxSeqLength;
+        t0 = std::chrono::steady_clock::now();
         // Like libmarv, every visible device is used (CUDA_VISIBLE_DEVICES selects them): the DB is cut into per-device slices and
         // each query is scanned against all slices at once (target-sharded, include/b200_multi.h).  B200_DEVICE=<id> pins one device;
         // the gapped rescoring mode needs the whole DB next to the scan and also stays on one device.
@@ -72,9 +74,14 @@ public:
             exit(EXIT_FAILURE);
         }
         ctx = b200_multi_ctx(multi, 0);
+        tCreate = elapsed();
     }
 
     ~Marv() {
+        if (getenv("B200_TRACE") != NULL) {
+            fprintf(stderr, "libb200align Marv: context %.3f s, loadDb %.3f s, %zu scans in %.3f s (%.3f ms each), lifetime %.3f s\n", tCreate,
+                    tLoad, nScans, tScan, nScans ? 1e3 * tScan / nScans : 0.0, elapsed());
+        }
         if (multi != NULL) {
             b200_multi_destroy(multi);
         }
@@ -94,9 +101,11 @@ public:
     // Masked residues become X, as the CPU scorer treats them (ungappedprefilter.cpp:401-404).
     void* loadDb(char* data, size_t* offset, int32_t* length, size_t dbByteSize) {
         (void) dbByteSize;
+        const double a = elapsed();
         const int rc = b200_multi_db_load_padded(multi, reinterpret_cast<const uint8_t*>(data), offset, length, dbEntries, alphabetSize,
                                                  /*shard_targets=*/1);
         checkMulti(rc, "loadDb");
+        tLoad = elapsed() - a;
         return this;
     }
 
@@ -126,6 +135,7 @@ public:
     Stats scan(const char* sequence, size_t sequenceLength, int8_t* pssm, Result* results) {
         Stats st;
         st.results = 0; st.numOverflows = 0; st.seconds = 0; st.gcups = 0;
+        const double a = elapsed();
         b200_query q;
         q.profile = pssm;
         q.qlen = (int32_t) sequenceLength;
@@ -167,10 +177,18 @@ public:
             }
         }
         st.results = n;
+        st.seconds = elapsed() - a;
+        tScan += st.seconds;
+        nScans++;
         return st;
     }
 
 private:
+    double elapsed() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+    std::chrono::steady_clock::time_point t0;
+    double tCreate = 0, tLoad = 0, tScan = 0;
+    size_t nScans = 0;
+
     void checkMulti(int rc, const char *what) {
         if (rc != B200_OK) {
             fprintf(stderr, "libb200align: %s failed (%d): %s\n", what, rc, b200_multi_last_error(multi));
