@@ -572,7 +572,7 @@ def main():
             roof["hbm"]["peak_gbs"] = 6650.0
             roof["hbm"]["peak_source"] = "fallback"
         try:   # DRAM traffic of the dominant launch, from the committed ncu capture of this same command
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["dominant"]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["dominant"]
             roof["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
             roof["traffic_note"] = "bytes of the longest scan launch of a step, %s (%d of the 16 queries), ncu capture in profiles/; algorithmic %d" % (
                 tr["kernel"], tr["queries_in_launch"], tr["algorithmic_bytes"])

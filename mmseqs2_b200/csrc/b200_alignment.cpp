@@ -476,12 +476,16 @@ int b200_align_batch(b200_ctx *ctx, const int16_t *sub_matrix, const double *p_b
 
     t_bt = Clock::now();
     // ---- getSWResult's assembly, checkCriteria, accept / reject walk, ordering (Matcher.cpp:84-141, Alignment.cpp:381-403) ----
-    uint64_t n_aln = 0, bt_used = 0;
-    std::vector<b200_result> acc;
-    std::vector<std::string> acc_bt;
-    for (uint32_t qi = 0; qi < n_queries; qi++) {
+    // Queries are independent: every host thread assembles, filters and orders the results of a range of queries; the
+    // backtrace strings are laid into the caller's pool in query order afterwards (the reference runs this loop under OpenMP too).
+    struct QueryOut { std::vector<b200_result> acc; std::vector<std::string> acc_bt; uint64_t n_aln = 0; int err = 0; };
+    std::vector<QueryOut> qout(n_queries);
+    parallel_ranges(n_queries, 4, [&](size_t q_first, size_t q_last) {
+    for (uint32_t qi = (uint32_t) q_first; qi < (uint32_t) q_last; qi++) {
         const int L = (int) (query_offsets[qi + 1] - query_offsets[qi]);
-        acc.clear(); acc_bt.clear();
+        std::vector<b200_result> &acc = qout[qi].acc;
+        std::vector<std::string> &acc_bt = qout[qi].acc_bt;
+        uint64_t &n_aln = qout[qi].n_aln;
         uint32_t passed = 0, rejected = 0;
         for (uint64_t k = hit_offsets[qi]; k < hit_offsets[qi + 1] && passed < params->max_accept && rejected < params->max_rejected; k++) {
             HitState &h = st[k];
@@ -490,7 +494,7 @@ int b200_align_batch(b200_ctx *ctx, const int16_t *sub_matrix, const double *p_b
             const uint32_t t = hit_targets[k];
             const int tl = db_len[t];
             if (h.identity) {          // SmithWaterman::scoreIdentical (StripedSmithWaterman.cpp:1770-1805)
-                if (tl != L) return b200_set_err(ctx, B200_ERR_ARG, "b200_align_batch: identity hit with a different length");
+                if (tl != L) { qout[qi].err = 1; break; }
                 short s = 0;
                 const uint8_t *ts = query_residues + query_offsets[qi];   // same key => same sequence as the query
                 for (int pos = 0; pos < L; pos++) s = (short) (s + profiles[qi][(size_t) ts[pos] * L + pos]);
@@ -548,17 +552,33 @@ int b200_align_batch(b200_ctx *ctx, const int16_t *sub_matrix, const double *p_b
                 if (a.db_len != b.db_len) return a.db_len < b.db_len;
                 return a.db_key < b.db_key;
             });
-        for (size_t i = 0; i < acc.size(); i++) {
-            const std::string &bt = acc_bt[(size_t) acc[i].bt_off];
-            if (bt_used + bt.size() > bt_cap || (bt.size() > 0 && bt_pool == nullptr))
-                return b200_set_err(ctx, B200_ERR_RANGE, "b200_align_batch: backtrace pool too small");
-            if (!bt.empty()) memcpy(bt_pool + bt_used, bt.data(), bt.size());
-            acc[i].bt_off = bt_used;
-            bt_used += bt.size();
-            results[hit_offsets[qi] + i] = acc[i];
-        }
-        n_results[qi] = (uint32_t) acc.size();
     }
+    });
+    uint64_t n_aln = 0, bt_used = 0;
+    std::vector<uint64_t> bt_base(n_queries + 1, 0);
+    for (uint32_t qi = 0; qi < n_queries; qi++) {
+        if (qout[qi].err) return b200_set_err(ctx, B200_ERR_ARG, "b200_align_batch: identity hit with a different length");
+        n_aln += qout[qi].n_aln;
+        uint64_t sz = 0;
+        for (const b200_result &r : qout[qi].acc) sz += r.bt_len;
+        bt_base[qi + 1] = bt_base[qi] + sz;
+    }
+    bt_used = bt_base[n_queries];
+    if (bt_used > bt_cap || (bt_used > 0 && bt_pool == nullptr)) return b200_set_err(ctx, B200_ERR_RANGE, "b200_align_batch: backtrace pool too small");
+    parallel_ranges(n_queries, 4, [&](size_t q_first, size_t q_last) {
+        for (size_t qi = q_first; qi < q_last; qi++) {
+            std::vector<b200_result> &acc = qout[qi].acc;
+            uint64_t at = bt_base[qi];
+            for (size_t i = 0; i < acc.size(); i++) {
+                const std::string &bt = qout[qi].acc_bt[(size_t) acc[i].bt_off];
+                if (!bt.empty()) memcpy(bt_pool + at, bt.data(), bt.size());
+                acc[i].bt_off = at;
+                at += bt.size();
+                results[hit_offsets[qi] + i] = acc[i];
+            }
+            n_results[qi] = (uint32_t) acc.size();
+        }
+    });
     if (n_alignments != nullptr) *n_alignments = n_aln;
     if (trace) {
         auto ms = [](Clock::time_point a, Clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };

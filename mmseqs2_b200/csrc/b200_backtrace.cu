@@ -280,14 +280,18 @@ int b200_sw_backtrace_impl(b200_ctx *ctx, const b200_query *queries, const uint8
     }
     const size_t m = h_tasks.size();
     if (m == 0) return B200_OK;
-    {   // longest alignments first: threads pull tasks from a counter, so the long ones must not start last
-        std::vector<uint32_t> ord(m);
-        for (size_t k = 0; k < m; k++) ord[k] = (uint32_t) k;
-        std::stable_sort(ord.begin(), ord.end(), [&h_tasks](uint32_t a, uint32_t b) {
-            return h_tasks[a].qend - h_tasks[a].qstart > h_tasks[b].qend - h_tasks[b].qstart; });
+    {   // longest alignments first: threads pull tasks from a counter, so the long ones must not start last.
+        // Stable counting sort on the query span (<= 65535): linear, where a comparison sort of 5e5 tasks cost ~60 ms per call.
+        std::vector<uint32_t> cnt(65537, 0);
+        for (size_t k = 0; k < m; k++) cnt[(size_t) std::min(65535, h_tasks[k].qend - h_tasks[k].qstart)]++;
+        uint32_t run = 0;
+        for (int v = 65535; v >= 0; v--) { const uint32_t c = cnt[v]; cnt[v] = run; run += c; }   // descending spans
         std::vector<BtTask> st(m);
         std::vector<uint64_t> si(m);
-        for (size_t k = 0; k < m; k++) { st[k] = h_tasks[ord[k]]; si[k] = idx[ord[k]]; }
+        for (size_t k = 0; k < m; k++) {
+            const uint32_t pos = cnt[(size_t) std::min(65535, h_tasks[k].qend - h_tasks[k].qstart)]++;
+            st[pos] = h_tasks[k]; si[pos] = idx[k];
+        }
         h_tasks.swap(st); idx.swap(si);
     }
 
