@@ -95,16 +95,15 @@ def main():
         t0 = time.perf_counter()
         res, off = gen_protein_db(torch, device, args.db3, seed=2)
         t_gen = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        ctx.load_db(res, off, 21)
-        t_load = time.perf_counter() - t0
         db_res = int(off[-1])
         rng = np.random.default_rng(1000 + rank)
         qres, qoff = synth.random_seqs(rng, args.q3, synth.background(pb), mean=350.0, sigma=35.0, lo=200, hi=500, normal=True)
         qs = synth.split(qres, qoff)
         # a few planted homologs so that the align step has survivors
         synth.plant_homologs(np.random.default_rng(3), res, off, qs[:8], synth.background(pb), frac=2000.0 / args.db3)
+        t0 = time.perf_counter()
         ctx.load_db(res, off, 21)
+        t_load = time.perf_counter() - t0
         profs = [sm.ssw_query(q) for q in qs]
         B = 16
         batches = [profs[i:i + B] for i in range(0, len(profs), B)]
