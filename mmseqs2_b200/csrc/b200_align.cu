@@ -217,6 +217,9 @@ ungapped_scan_kernel(const int8_t *__restrict__ raw, const QueryDesc *__restrict
             }
 #pragma unroll
             for (int u = 0; u < 16; u += 2) {
+                // the columns beyond the longest target of the warp are pad residues (neutral row): the second half of the last
+                // 16-column chunk is skipped when nothing real is in it (8-column granularity of the loop end, ~1 % fewer cells)
+                if (!TILED && u == 8 && i0 + 8 >= maxl) break;
                 const uint32_t wv = cw[u >> 2];
                 const uint32_t a0 = (wv >> (8 * (u & 3))) & 0xffu;
                 const uint32_t a1 = (wv >> (8 * ((u + 1) & 3))) & 0xffu;
