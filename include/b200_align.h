@@ -84,6 +84,10 @@ int b200_db_load(b200_ctx *ctx, const uint8_t *residues, const uint64_t *offsets
  * data[offsets[i] .. offsets[i] + lengths[i]), numeric codes with +32 marking soft-masked residues, which become X = alphabet-1 as
  * in the CPU scorer (ungappedprefilter.cpp:401-404). */
 int b200_db_load_padded(b200_ctx *ctx, const uint8_t *data, const size_t *offsets, const int32_t *lengths, uint64_t n_seq, int alphabet);
+/* The same layout with the mask bit stripped instead (code - 32): the residues Sequence::mapSequence yields for a padded DB read back
+ * through DBReader::getUnpadded (src/commons/DBReader.cpp:349-371: masked letters come back lower-case and map to the same codes) -- what
+ * the `align` module scores against. */
+int b200_db_load_padded_unmasked(b200_ctx *ctx, const uint8_t *data, const size_t *offsets, const int32_t *lengths, uint64_t n_seq, int alphabet);
 uint64_t b200_db_num_seqs(const b200_ctx *ctx);
 uint64_t b200_db_num_residues(const b200_ctx *ctx);
 

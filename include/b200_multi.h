@@ -45,6 +45,9 @@ int b200_multi_db_load(b200_multi *m, const uint8_t *residues, const uint64_t *o
 /* the padded GPU DB of makepaddedseqdb as Marv::loadDb takes it (b200_db_load_padded) */
 int b200_multi_db_load_padded(b200_multi *m, const uint8_t *data, const size_t *offsets, const int32_t *lengths, uint64_t n_seq,
                               int alphabet, int shard_targets);
+/* replicated, mask bit stripped (b200_db_load_padded_unmasked): the target DB of the `align` module */
+int b200_multi_db_load_padded_unmasked(b200_multi *m, const uint8_t *data, const size_t *offsets, const int32_t *lengths, uint64_t n_seq,
+                                       int alphabet);
 
 /* b200_ungapped_scan over all devices; hits [n_queries][max_hits], n_hits [n_queries], global target ids. */
 int b200_multi_ungapped_scan(b200_multi *m, const b200_query *queries, int n_queries, int min_score_excl, uint32_t max_hits,

@@ -96,27 +96,41 @@ static inline bool alignOnDevice(DBReader<DBKeyType> *qdbr, DBReader<DBKeyType> 
         tOff[i + 1] = tOff[i] + tdbr->getSeqLen(i);
         tKeys[i] = (uint32_t) tdbr->getDbKey(i);
     }
-    std::vector<uint8_t> tRes(tOff[nT] + 1);
-#pragma omp parallel num_threads(threads)
-    {
-        unsigned int thread_idx = 0;
-#ifdef OPENMP
-        thread_idx = static_cast<unsigned int>(omp_get_thread_num());
-#endif
-        Sequence dbSeq(s.maxSeqLen, targetSeqType, m, 0, false, s.compBiasCorrection);
-#pragma omp for schedule(dynamic, 1000)
+    int rc;
+    double tMap = 0;
+    const bool paddedDb = (DBReader<DBKeyType>::getExtendedDbtype(tdbr->getDbtype()) & Parameters::DBTYPE_EXTENDED_GPU) != 0;
+    if (paddedDb && tdbr->getDataFileCnt() == 1) {
+        // the padded GPU DB already holds numeric codes (makepaddedseqdb.cpp:77-86): hand it over as it lies, mask bit stripped --
+        // the residues Sequence::mapSequence would produce from DBReader::getUnpadded, without touching every sequence on the host
+        std::vector<size_t> pOff(nT);
+        std::vector<int32_t> pLen(nT);
         for (size_t i = 0; i < nT; i++) {
-            dbSeq.mapSequence(i, tKeys[i], tdbr->getData(i, thread_idx), tdbr->getSeqLen(i));
-            memcpy(tRes.data() + tOff[i], dbSeq.numSequence, (size_t) dbSeq.L);
+            pOff[i] = tdbr->getOffset(i);
+            pLen[i] = (int32_t) tdbr->getSeqLen(i);
         }
+        rc = b200_multi_db_load_padded_unmasked(multi, reinterpret_cast<const uint8_t *>(tdbr->getDataForFile(0)), pOff.data(), pLen.data(), nT, A);
+    } else {
+        std::vector<uint8_t> tRes(tOff[nT] + 1);
+#pragma omp parallel num_threads(threads)
+        {
+            unsigned int thread_idx = 0;
+#ifdef OPENMP
+            thread_idx = static_cast<unsigned int>(omp_get_thread_num());
+#endif
+            Sequence dbSeq(s.maxSeqLen, targetSeqType, m, 0, false, s.compBiasCorrection);
+#pragma omp for schedule(dynamic, 1000)
+            for (size_t i = 0; i < nT; i++) {
+                dbSeq.mapSequence(i, tKeys[i], tdbr->getData(i, thread_idx), tdbr->getSeqLen(i));
+                memcpy(tRes.data() + tOff[i], dbSeq.numSequence, (size_t) dbSeq.L);
+            }
+        }
+        tMap = since(tStart) - tCreate;
+        rc = b200_multi_db_load(multi, tRes.data(), tOff.data(), nT, A, /*shard_targets=*/0);
     }
-    const double tMap = since(tStart) - tCreate;
-    int rc = b200_multi_db_load(multi, tRes.data(), tOff.data(), nT, A, /*shard_targets=*/0);
     if (rc != B200_OK) {
         Debug(Debug::ERROR) << "libb200align: b200_db_load failed: " << b200_multi_last_error(multi) << "\n";
         EXIT(EXIT_FAILURE);
     }
-    std::vector<uint8_t>().swap(tRes);
     const double tLoad = since(tStart) - tCreate - tMap;
     double tParse = 0, tDevice = 0, tWrite = 0;
 

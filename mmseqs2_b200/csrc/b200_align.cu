@@ -1232,7 +1232,7 @@ int b200_sync(b200_ctx *ctx) {
 // residues (ungappedprefilter.cpp:401-404); mask_from = 256 disables that.  The re-layout (16-byte aligned, padded with code
 // `alphabet`) runs on all host threads: at 20 M sequences this is 7.5 GB of bytes.
 int b200_db_load_impl(b200_ctx *ctx, const uint8_t *base, const uint64_t *starts, const int32_t *lens, uint64_t n_seq, int alphabet,
-                      int mask_from, uint64_t n_res) {
+                      int mask_from, uint64_t n_res, bool strip_mask) {
     CU_TRY(ctx, cudaSetDevice(ctx->device));
     db_free(ctx);
     std::vector<uint64_t> h_off(n_seq);
@@ -1261,7 +1261,7 @@ int b200_db_load_impl(b200_ctx *ctx, const uint8_t *base, const uint64_t *starts
                     uint8_t *dst = h_res + h_off[i];
                     for (int32_t j = 0; j < lens[i]; j++) {
                         uint8_t c = src[j];
-                        if (c >= mask_from) c = (uint8_t) (alphabet - 1);
+                        if (c >= mask_from) c = strip_mask ? (uint8_t) (c - 32) : (uint8_t) (alphabet - 1);
                         if (c >= alphabet) bad[t] = 1;
                         dst[j] = c;
                     }
@@ -1309,10 +1309,11 @@ int b200_db_load(b200_ctx *ctx, const uint8_t *residues, const uint64_t *offsets
         if (l > 65535) return set_err(ctx, B200_ERR_RANGE, "b200_db_load: sequence longer than 65535 (maxSeqLen)");
         lens[i] = (int32_t) l;
     }
-    return b200_db_load_impl(ctx, residues, offsets, lens.data(), n_seq, alphabet, 256, offsets[n_seq] - offsets[0]);
+    return b200_db_load_impl(ctx, residues, offsets, lens.data(), n_seq, alphabet, 256, offsets[n_seq] - offsets[0], false);
 }
 
-int b200_db_load_padded(b200_ctx *ctx, const uint8_t *data, const size_t *offsets, const int32_t *lengths, uint64_t n_seq, int alphabet) {
+static int db_load_padded_common(b200_ctx *ctx, const uint8_t *data, const size_t *offsets, const int32_t *lengths, uint64_t n_seq, int alphabet,
+                                 bool strip_mask) {
     if (ctx == nullptr) return B200_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (data == nullptr || offsets == nullptr || lengths == nullptr || n_seq == 0 || alphabet <= 0 || alphabet > 31)
@@ -1325,7 +1326,15 @@ int b200_db_load_padded(b200_ctx *ctx, const uint8_t *data, const size_t *offset
         starts[i] = offsets[i];
         n_res += (uint64_t) lengths[i];
     }
-    return b200_db_load_impl(ctx, data, starts.data(), lengths, n_seq, alphabet, 32, n_res);
+    return b200_db_load_impl(ctx, data, starts.data(), lengths, n_seq, alphabet, 32, n_res, strip_mask);
+}
+
+int b200_db_load_padded(b200_ctx *ctx, const uint8_t *data, const size_t *offsets, const int32_t *lengths, uint64_t n_seq, int alphabet) {
+    return db_load_padded_common(ctx, data, offsets, lengths, n_seq, alphabet, false);
+}
+
+int b200_db_load_padded_unmasked(b200_ctx *ctx, const uint8_t *data, const size_t *offsets, const int32_t *lengths, uint64_t n_seq, int alphabet) {
+    return db_load_padded_common(ctx, data, offsets, lengths, n_seq, alphabet, true);
 }
 
 int b200_device_count(void) {

@@ -117,7 +117,7 @@ int b200_sw_backtrace_impl(b200_ctx *ctx, const b200_query *queries, const uint8
 
 // common body of b200_db_load / b200_db_load_padded / b200_db_load_ascii (b200_align.cu); the caller holds ctx->mu
 int b200_db_load_impl(b200_ctx *ctx, const uint8_t *base, const uint64_t *starts, const int32_t *lens, uint64_t n_seq, int alphabet,
-                      int mask_from, uint64_t n_res);
+                      int mask_from, uint64_t n_res, bool strip_mask);
 
 void b200_ascii_db_free(b200_ctx *ctx);   // b200_rescore.cu
 

@@ -137,6 +137,17 @@ int b200_multi_db_load_padded(b200_multi *m, const uint8_t *data, const size_t *
     });
 }
 
+int b200_multi_db_load_padded_unmasked(b200_multi *m, const uint8_t *data, const size_t *offsets, const int32_t *lengths, uint64_t n_seq, int alphabet) {
+    if (m == nullptr) return B200_ERR_ARG;
+    if (data == nullptr || offsets == nullptr || lengths == nullptr || n_seq == 0) return fail(m, B200_ERR_ARG, "b200_multi_db_load_padded_unmasked: bad arguments");
+    const int nd = (int) m->ctx.size();
+    m->shard_targets = false;
+    m->n_seq = n_seq;
+    m->tgt_begin.assign(nd + 1, 0);
+    m->tgt_begin[nd] = n_seq;
+    return on_every_device(m, [&](int d) { return b200_db_load_padded_unmasked(m->ctx[d], data, offsets, lengths, n_seq, alphabet); });
+}
+
 int b200_multi_ungapped_scan(b200_multi *m, const b200_query *queries, int nq, int min_score_excl, uint32_t max_hits, b200_hit *hits,
                              uint32_t *n_hits) {
     if (m == nullptr) return B200_ERR_ARG;
