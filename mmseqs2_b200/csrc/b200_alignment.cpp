@@ -396,16 +396,22 @@ int b200_align_batch(b200_ctx *ctx, const int16_t *sub_matrix, const double *p_b
     std::vector<b200_pair> epairs;
     std::vector<int32_t> escores;
     std::vector<uint64_t> ehit;
-    for (uint64_t i = 0; i < np; i++) {
-        HitState &h = st[pair_hit[i]];
-        const int L = queries[pairs[i].query].qlen;
-        h.score1 = (uint32_t) scores[i]; h.q_end = L - 1; h.db_end = -1;
-        if (scores[i] <= 0) continue;          // "no residue could be aligned": the reference returns uninitialised fields
-        h.defined = true;
-        h.evalue = b200h_evalue(evalue, (double) h.score1, (double) L);
-        if (h.evalue > params->eval_thr) continue;
-        epairs.push_back(pairs[i]); escores.push_back(scores[i]); ehit.push_back(pair_hit[i]);
-    }
+    // the E-value of every scored pair (ALP's finite-size-corrected area: a few exp/log per call) on all host threads, then the ordered
+    // compaction of the pairs that pass
+    std::vector<uint8_t> pass(np, 0);
+    parallel_ranges(np, 4096, [&](size_t a, size_t b) {
+        for (size_t i = a; i < b; i++) {
+            HitState &h = st[pair_hit[i]];
+            const int L = queries[pairs[i].query].qlen;
+            h.score1 = (uint32_t) scores[i]; h.q_end = L - 1; h.db_end = -1;
+            if (scores[i] <= 0) continue;          // "no residue could be aligned": the reference returns uninitialised fields
+            h.defined = true;
+            h.evalue = b200h_evalue(evalue, (double) h.score1, (double) L);
+            pass[i] = h.evalue > params->eval_thr ? 0 : 1;
+        }
+    });
+    for (uint64_t i = 0; i < np; i++)
+        if (pass[i]) { epairs.push_back(pairs[i]); escores.push_back(scores[i]); ehit.push_back(pair_hit[i]); }
     std::vector<b200_sw_end> ends(epairs.size());
     if (!epairs.empty()) {
         int rc = b200_sw_endpos(ctx, queries.data(), (int) n_queries, epairs.data(), epairs.size(), go, ge, escores.data(), ends.data());
