@@ -8,7 +8,7 @@ config[3]  full easy-search shape: queries vs a 20 M-sequence UniRef-shaped synt
            linear in queries): ungapped prefilter of every query against the whole DB, then the `align` step (-a, -e 1e-3) on the hit
            lists; hit lists gathered with one NCCL all_gather per batch (pipelined as in bench.py).
 config[4]  nucleotide mode: 150-bp reads (2 % substitutions, 0.2 % indels, both strands) sampled from a 5 Gbp synthetic genome cut
-           into <= 65 535-bp targets, genome replicated on every GPU, reads sharded by rank (1 M reads / N per rank), gapped
+           into 32 000-bp targets (the aligner's limit is 32 767; `splitsequence` cuts longer ones upstream), genome replicated on every GPU, reads sharded by rank (1 M reads / N per rank), gapped
            nucleotide aligner on the prefilter diagonal of every read (nucleotide.out, gap 5/2, zdrop 40, band 64).
 
 Synthetic data is generated on the GPU with torch (data plumbing: 7e9 residues take minutes in numpy) and handed to the library as
@@ -151,11 +151,15 @@ def main():
         for j in jobs:
             j.close()
         del res, off
+        if rank == 0:      # keep what is done even if a later part fails
+            os.makedirs(os.path.dirname(args.out), exist_ok=True)
+            json.dump(out, open(args.out, "w"), indent=1)
+            print(json.dumps(out), flush=True)
 
     # ---------------------------------------------------------------------------------------------------------------- config[4]
     if not args.skip4:
         t0 = time.perf_counter()
-        tl = 65535
+        tl = 32000          # b200_nucl_align takes sequences up to 32767 (longer ones are split upstream, blastn.sh:27-52)
         n_t = int(args.genome // tl)
         g = torch.Generator(device=device); g.manual_seed(5)
         genome = np.empty(n_t * tl, np.uint8)
