@@ -584,6 +584,12 @@ def main():
             roof["frac"] = achieved_ops / peak
             roof["dpx_thread_instr_per_clk_per_sm"] = dpx
             roof["clock_mhz_used"] = clk_mhz
+        # the resource that actually binds (ncu: l1tex data-pipe wavefronts 92-98 % of peak): 2 B of profile per cell through
+        # the 128 B/clk/SM shared-memory pipe (LDS.128 measured at 8.0 per clk per SM by the same microbenchmark)
+        lds = rates.get("LDS.128")
+        smem_peak_gcups = (lds or 8.0) * 16.0 / 2.0 * info["sm_count"] * clk_mhz * 1e6 / 1e9
+        roof["binding_resource"] = {"name": "shared-memory pipe", "bytes_per_cell": 2.0, "lds128_per_clk_per_sm": lds or 8.0,
+                                    "peak_gcups": smem_peak_gcups, "frac": roof["kernel_gcups"] / smem_peak_gcups}
         line["roofline"] = roof
 
         # ---- secondary: the whole hot path of `search --prefilter-mode 1` for one query batch, host buffers end to end:
