@@ -492,7 +492,8 @@ def main():
     run_steps(args.warmup)
     barrier()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:          # the line is rank 0's; eight ranks forking nvidia-smi ten times a second only load the host
+        sampler.start()
     launches0 = ctx.launches
     ctx.event_record(0)
     t_wall0 = time.perf_counter()
@@ -502,7 +503,7 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     dev_ms = ctx.event_elapsed_ms(0, 1)
     launches = ctx.launches - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if rank == 0 else {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
     step_ms = (t_wall * 1e3 if dist is not None else dev_ms)
     # kernel-only time of the scan kernel for the roofline (events around the launches of one job, no fetch)
     ctx.event_record(2)
