@@ -11,6 +11,7 @@ Reference interface            ->  here
   SmithWaterman::ssw_align (modes 0/1)                               Context.sw_align()
 """
 import ctypes
+import weakref
 import os
 
 import numpy as np
@@ -150,6 +151,7 @@ def _cqueries(queries):
 class Job:
     def __init__(self, ctx, handle, kind, nq=0, k=0, n=0):
         self.ctx, self.handle, self.kind, self.nq, self.k, self.n = ctx, handle, kind, nq, k, n
+        ctx._jobs.add(self)        # a job must not outlive its context: Context.close() destroys what is still open
 
     def run(self):
         self.ctx._check(self.ctx.lib.b200_job_run(self.handle))
@@ -176,8 +178,10 @@ class Job:
 
     def close(self):
         if self.handle:
-            self.ctx.lib.b200_job_destroy(self.handle)
+            if getattr(self.ctx, "h", None):      # the context is still alive (b200_job_destroy touches its stream and mutex)
+                self.ctx.lib.b200_job_destroy(self.handle)
             self.handle = None
+            self.ctx._jobs.discard(self)
 
     def __del__(self):
         try:
@@ -197,9 +201,12 @@ class Context:
             raise B200Error("b200_create(%d) failed with %d (is a CUDA device visible?)" % (device, rc))
         self.h = h
         self.n_seq = 0
+        self._jobs = weakref.WeakSet()
 
     def close(self):
         if getattr(self, "h", None):
+            for j in list(self._jobs):
+                j.close()
             self.lib.b200_destroy(self.h)
             self.h = None
 
