@@ -352,6 +352,91 @@ topk_select_kernel(const uint8_t *__restrict__ dense, uint32_t n_seq, int thr, u
     if (threadIdx.x == 0) n_hits[blockIdx.x] = s_total;
 }
 
+// The same selection spread over TOPK_PARTS CTAs per query, for callers that scan one query at a time (Marv::scan is called once per
+// query, ungappedprefilter.cpp:207): a single CTA walking 1 M scores costs ~1.5 ms, a fifth of the scan itself.
+//   topk_hist_kernel     CTA (query, part): 256-bin histogram of its slice of the score vector -> part_hist[q][part][256]
+//   topk_compact_kernel  CTA (query, part): cut-off from the summed histograms, the slice's base ranks from the parts before it,
+//                        ordered compaction of the slice -- the output is identical to topk_select_kernel's (ids ascending within
+//                        "above the cut" and within "ties at the cut").
+constexpr int TOPK_PARTS = 64;
+
+__global__ void __launch_bounds__(256)
+topk_hist_kernel(const uint8_t *__restrict__ dense, uint32_t n_seq, uint32_t *__restrict__ part_hist) {
+    __shared__ uint32_t hist[256];
+    const uint32_t q = blockIdx.y, part = blockIdx.x;
+    const uint32_t per = ((n_seq + TOPK_PARTS - 1) / TOPK_PARTS + 15) / 16 * 16;
+    const uint32_t a = min(n_seq, part * per), b = min(n_seq, a + per);
+    const uint8_t *sc = dense + (size_t) q * n_seq;
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = a + threadIdx.x; i < b; i += blockDim.x) atomicAdd(&hist[sc[i]], 1u);
+    __syncthreads();
+    part_hist[((size_t) q * TOPK_PARTS + part) * 256 + threadIdx.x] = hist[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256)
+topk_compact_kernel(const uint8_t *__restrict__ dense, uint32_t n_seq, int thr, uint32_t k, const uint32_t *__restrict__ part_hist,
+                    b200_hit *__restrict__ hits, uint32_t *__restrict__ n_hits) {
+    __shared__ uint32_t total[256], before[256];
+    __shared__ uint32_t warp_sums[8][2];
+    __shared__ int s_cut;
+    __shared__ uint32_t s_need, s_total, s_base_hi, s_base_tie;
+    const uint32_t q = blockIdx.y, part = blockIdx.x;
+    const uint32_t per = ((n_seq + TOPK_PARTS - 1) / TOPK_PARTS + 15) / 16 * 16;
+    const uint32_t a = min(n_seq, part * per), b = min(n_seq, a + per);
+    const uint8_t *sc = dense + (size_t) q * n_seq;
+    b200_hit *oh = hits + (size_t) q * k;
+    {   // per bin: count over all parts, and over the parts before this one
+        uint32_t t = 0, bf = 0;
+        const uint32_t *ph = part_hist + (size_t) q * TOPK_PARTS * 256 + threadIdx.x;
+        for (uint32_t p2 = 0; p2 < TOPK_PARTS; p2++) { const uint32_t c = ph[(size_t) p2 * 256]; t += c; if (p2 < part) bf += c; }
+        total[threadIdx.x] = t; before[threadIdx.x] = bf;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t cum = 0;
+        int cut = thr;  // keep everything > cut, plus `need` smallest-id entries == cut
+        uint32_t need = 0;
+        for (int s = 255; s > thr; s--) {
+            if (cum + total[s] > k) { cut = s; need = k - cum; break; }
+            cum += total[s];
+        }
+        uint32_t bh = 0;
+        for (int s = 255; s > cut; s--) bh += before[s];
+        s_cut = cut; s_need = need; s_total = cum + need; s_base_hi = bh; s_base_tie = (need > 0 && cut >= 0) ? before[cut] : 0;
+    }
+    __syncthreads();
+    const int cut = s_cut;
+    const uint32_t need = s_need;
+    const bool take_ties = need > 0;
+    const uint32_t n_hi_total = s_total - need;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t i0 = a; i0 < b; i0 += blockDim.x) {
+        const uint32_t i = i0 + threadIdx.x;
+        const int s = (i < b) ? (int) sc[i] : -0x7fffffff;
+        const bool hi = s > cut;
+        const bool tie = take_ties && s == cut;
+        const unsigned bhm = __ballot_sync(0xffffffffu, hi), btm = __ballot_sync(0xffffffffu, tie);
+        if (lane == 0) { warp_sums[wid][0] = __popc(bhm); warp_sums[wid][1] = __popc(btm); }
+        __syncthreads();
+        uint32_t pre_h = 0, pre_t = 0;
+        for (int w = 0; w < wid; w++) { pre_h += warp_sums[w][0]; pre_t += warp_sums[w][1]; }
+        const uint32_t lm = (1u << lane) - 1u;
+        const uint32_t rh = s_base_hi + pre_h + __popc(bhm & lm);
+        const uint32_t rt = s_base_tie + pre_t + __popc(btm & lm);
+        if (hi) { oh[rh].id = i; oh[rh].score = s; }
+        if (tie && rt < need) { oh[n_hi_total + rt].id = i; oh[n_hi_total + rt].score = s; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t th = 0, tt = 0;
+            for (int w = 0; w < (int) (blockDim.x >> 5); w++) { th += warp_sums[w][0]; tt += warp_sums[w][1]; }
+            s_base_hi += th; s_base_tie += tt;
+        }
+        __syncthreads();
+    }
+    if (part == 0 && threadIdx.x == 0) n_hits[q] = s_total;
+}
+
 // ------------------------------------------------------------------------------------------------
 // A1: per-diagonal scorer.  UngappedAlignment.cpp:45-57 (scalarDiagonalScoring), :423-437 (segment selection),
 // :283 (min(255,.)).  max over prefixes of the 0-reset running sum == maximum-subarray sum, which is associative:
@@ -1104,7 +1189,7 @@ struct b200_job {
     uint32_t k = 0;
     std::vector<int> cfg_of_query;             // per query
     std::vector<std::vector<int>> cfg_groups;  // query indices per configuration (launch groups)
-    DevBuf raw, qdesc, qdesc_grouped, dense, hits, nhits, pad;
+    DevBuf raw, qdesc, qdesc_grouped, dense, hits, nhits, pad, part_hist;
     std::vector<int> grouped_order;  // position -> original query index
     // sw
     uint64_t n_pairs = 0;
@@ -1131,7 +1216,7 @@ struct b200_job {
         if (done) { cudaEventDestroy(done); done = nullptr; }
         for (Part *pt : parts) { pt->pairs.release(); pt->items.release(); pt->out.release(); delete pt; }
         parts.clear();
-        raw.release(); qdesc.release(); qdesc_grouped.release(); dense.release(); hits.release(); nhits.release();
+        raw.release(); qdesc.release(); qdesc_grouped.release(); dense.release(); hits.release(); nhits.release(); part_hist.release();
         pad.release(); pairs.release(); items.release(); out4.release(); bnd.release();
     }
 };
@@ -1439,9 +1524,19 @@ static int scan_job_run_locked(b200_job *job) {
             CU_TRY(ctx, cudaEventRecord(ctx->ev_join[k], ctx->side[k]));
             CU_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0));
         }
-    topk_select_kernel<<<job->nq, 1024, 0, ctx->stream>>>(job->dense.as<uint8_t>(), (uint32_t) ctx->n_seq, job->thr, job->k,
-                                                          job->hits.as<b200_hit>(), job->nhits.as<uint32_t>());
-    ctx->launches++;
+    if ((uint64_t) job->nq * TOPK_PARTS <= 4096 && ctx->n_seq >= 65536 && getenv("B200_TOPK_SINGLE") == nullptr) {
+        // few queries, many targets: the selection spread over TOPK_PARTS CTAs per query (identical output, ~30x shorter critical path)
+        CU_TRY(ctx, job->part_hist.reserve(sizeof(uint32_t) * 256 * TOPK_PARTS * (size_t) job->nq));
+        const dim3 grid(TOPK_PARTS, (unsigned) job->nq);
+        topk_hist_kernel<<<grid, 256, 0, ctx->stream>>>(job->dense.as<uint8_t>(), (uint32_t) ctx->n_seq, job->part_hist.as<uint32_t>());
+        topk_compact_kernel<<<grid, 256, 0, ctx->stream>>>(job->dense.as<uint8_t>(), (uint32_t) ctx->n_seq, job->thr, job->k,
+                                                            job->part_hist.as<uint32_t>(), job->hits.as<b200_hit>(), job->nhits.as<uint32_t>());
+        ctx->launches += 2;
+    } else {
+        topk_select_kernel<<<job->nq, 1024, 0, ctx->stream>>>(job->dense.as<uint8_t>(), (uint32_t) ctx->n_seq, job->thr, job->k,
+                                                              job->hits.as<b200_hit>(), job->nhits.as<uint32_t>());
+        ctx->launches++;
+    }
     CU_TRY(ctx, cudaGetLastError());
     if (job->done == nullptr) CU_TRY(ctx, cudaEventCreateWithFlags(&job->done, cudaEventDisableTiming));
     CU_TRY(ctx, cudaEventRecord(job->done, ctx->stream));
