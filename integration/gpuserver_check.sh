@@ -8,7 +8,7 @@ HERE="$(cd "$(dirname "$0")" && pwd)"
 B="$HERE/_build/mmseqs_b200"; C="$HERE/_build/mmseqs_avx2"; W=${1:-/tmp/gpusrv}; EX="$HERE/_build/examples"
 rm -rf "$W"; mkdir -p "$W"; cd "$W"
 "$C" createdb "$EX/QUERY.fasta" Q -v 1 >/dev/null; "$C" createdb "$EX/DB.fasta" T -v 1 >/dev/null; "$C" makepaddedseqdb T T_pad -v 1 >/dev/null
-timeout 120 "$B" gpuserver T_pad --max-seqs 300 -v 3 > server.log 2>&1 &
+timeout 120 "$B" gpuserver T_pad --max-seqs 300 > server.log 2>&1 &
 SRV=$!
 sleep 6
 timeout 90 "$B" ungappedprefilter Q T_pad pref_srv --gpu 1 --gpu-server 1 --threads 4 -v 2 > client.log 2>&1; echo "client exit $?"
