@@ -8,8 +8,9 @@
  *                 (SubstitutionMatrix::setupLetterMapping, SubstitutionMatrix.cpp:257-298; NucleotideMatrix.cpp:17-62)
  *
  * and b200_align_db: the `align` module over DB files -- query DB + target DB + prefilter result DB -> alignment result DB --
- * built on b200_align_batch (include/b200_alignment.h).  Uncompressed, single-part or ".0 .1 ..." split data files; no lookup /
- * source / header files (not needed by the path).  Plain C ABI, status codes, no exceptions.
+ * built on b200_align_batch (include/b200_alignment.h).  Single-part or ".0 .1 ..." split data files, plain or zstd-compressed
+ * (dbtype bit 31, DBReader::getDataCompressed, src/commons/DBReader.cpp:575-607: inflated at open through a run-time dlopen of
+ * libzstd.so.1, b200h_db_type reports the plain type); no lookup / source / header files (not needed by the path).  Plain C ABI, status codes, no exceptions.
  */
 #ifndef B200_DB_H
 #define B200_DB_H

@@ -23,7 +23,7 @@ def build(force=False, verbose=False):
         return SO
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-I" + os.path.join(ROOT, "include"),
-           "-o", SO] + SOURCES + ["-lrt"]
+           "-o", SO] + SOURCES + ["-lrt", "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd)

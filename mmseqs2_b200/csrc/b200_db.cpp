@@ -8,6 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
+#include <mutex>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -33,6 +36,92 @@ bool read_file(const std::string &path, std::vector<char> &out) {
 }
 
 struct IndexEntry { uint32_t key; uint64_t offset; uint64_t length; };
+
+// zstd streaming decompression, bound at run time: compressed DBs (createdb --compressed 1, `mmseqs compress`) are the only users,
+// so the library carries no load-time dependency on libzstd.  The two buffer structs are zstd's stable public ABI (zstd.h,
+// "Streaming decompression"): { pointer, size, pos }.
+struct ZInBuf { const void *src; size_t size; size_t pos; };
+struct ZOutBuf { void *dst; size_t size; size_t pos; };
+struct Zstd {
+    void *(*createDStream)() = nullptr;
+    size_t (*initDStream)(void *) = nullptr;
+    size_t (*decompressStream)(void *, ZOutBuf *, ZInBuf *) = nullptr;
+    size_t (*freeDStream)(void *) = nullptr;
+    unsigned (*isError)(size_t) = nullptr;
+    bool ok = false;
+};
+
+const Zstd &zstd_api() {
+    static Zstd z;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_LOCAL);
+        if (h == nullptr) h = dlopen("libzstd.so", RTLD_NOW | RTLD_LOCAL);
+        if (h == nullptr) return;
+        z.createDStream = (void *(*)()) dlsym(h, "ZSTD_createDStream");
+        z.initDStream = (size_t (*)(void *)) dlsym(h, "ZSTD_initDStream");
+        z.decompressStream = (size_t (*)(void *, ZOutBuf *, ZInBuf *)) dlsym(h, "ZSTD_decompressStream");
+        z.freeDStream = (size_t (*)(void *)) dlsym(h, "ZSTD_freeDStream");
+        z.isError = (unsigned (*)(size_t)) dlsym(h, "ZSTD_isError");
+        z.ok = z.createDStream && z.initDStream && z.decompressStream && z.freeDStream && z.isError;
+    });
+    return z;
+}
+
+// A compressed DB (dbtype bit 31) stores every entry as  [uint32 n][n payload bytes][marker]  with the index keeping the entry's
+// offset and its UNCOMPRESSED length + 1 (DBWriter::writeEnd, src/commons/DBWriter.cpp:372-413): marker 0 = the payload is one zstd
+// frame, anything else (0xFF) = the payload is the text itself, stored raw because it was shorter than 60 bytes.  The reader tells
+// the two apart by that marker byte (DBReader::getDataCompressed, src/commons/DBReader.cpp:575-607).  Rewrites `data` / `index`
+// into the plain layout (text + NUL back to back) the rest of this file works on.
+bool inflate_db(std::vector<char> &data, std::vector<IndexEntry> &index, std::string &err) {
+    const Zstd &z = zstd_api();
+    if (!z.ok) { err = "compressed DB needs libzstd.so.1 at run time (dlopen failed)"; return false; }
+    const uint64_t data_size = data.size() - 1;
+    uint64_t total = 0;
+    for (const IndexEntry &e : index) total += e.length;
+    std::vector<char> plain;
+    void *ds = z.createDStream();
+    if (ds == nullptr) { err = "ZSTD_createDStream failed"; return false; }
+    bool ok = true;
+    try {
+    plain.reserve(total + 1);
+    for (IndexEntry &e : index) {
+        if (e.offset + 5 > data_size) { err = "compressed entry beyond the data file"; ok = false; break; }
+        uint32_t n;
+        memcpy(&n, data.data() + e.offset, 4);
+        const char *payload = data.data() + e.offset + 4;
+        if ((uint64_t) n + 1 > data_size - e.offset - 4) { err = "compressed entry beyond the data file"; ok = false; break; }
+        const uint64_t at = plain.size();
+        const uint64_t want = e.length - 1;
+        if (payload[n] == 0) {
+            plain.resize(at + want + 1);
+            z.initDStream(ds);
+            ZInBuf in = {payload, n, 0};
+            ZOutBuf out = {plain.data() + at, (size_t) want, 0};
+            while (in.pos < in.size) {
+                const size_t before_in = in.pos, before_out = out.pos;
+                const size_t rc = z.decompressStream(ds, &out, &in);
+                if (z.isError(rc)) { err = "zstd: corrupt entry"; ok = false; break; }
+                if (rc == 0) break;                                              // frame complete
+                if (in.pos == before_in && out.pos == before_out) { err = "zstd: entry longer than its index length"; ok = false; break; }
+            }
+            if (!ok) break;
+            if (out.pos != want) { err = "zstd: entry shorter than its index length"; ok = false; break; }
+            plain[at + want] = '\0';
+        } else {
+            if (n != want) { err = "raw entry of a compressed DB disagrees with its index length"; ok = false; break; }
+            plain.insert(plain.end(), payload, payload + n);
+            plain.push_back('\0');
+        }
+        e.offset = at;
+    }
+    } catch (const std::bad_alloc &) { err = "compressed DB: index lengths exceed the memory available"; ok = false; }
+    z.freeDStream(ds);
+    if (!ok) return false;
+    plain.push_back('\0');
+    data.swap(plain);
+    return true;
+}
 
 }  // namespace
 
@@ -67,6 +156,17 @@ int b200h_db_open(const char *data_path, b200h_db **out) {
         if (parts == 0) { delete db; return db_fail("cannot open data file " + base); }
     }
     db->data.push_back('\0');
+    bool compressed = false;
+    std::vector<char> ty;
+    if (read_file(base + ".dbtype", ty) && ty.size() >= 4) {
+        int32_t v; memcpy(&v, ty.data(), 4);
+        // extended flag 8 = GPU-padded residues (Parameters.h:94): that layout is read by b200_db_load_padded from the caller's
+        // DBReader, not as text through this reader -- refuse instead of misreading it
+        const uint32_t ext = ((uint32_t) v >> 16) & 0x7FFEu;                       // DBReader::getExtendedDbtype
+        if ((ext & 8u) != 0) { delete db; return db_fail("GPU-padded DB: not supported by b200h_db_open: " + base); }
+        compressed = ((uint32_t) v & (1u << 31)) != 0;                             // DBReader::isCompressed
+        db->dbtype = (int32_t) ((uint32_t) v & ~(1u << 31));                       // what callers see is the plain DB
+    }
     std::vector<char> idx;
     if (!read_file(base + ".index", idx)) { delete db; return db_fail("cannot open index file " + base + ".index"); }
     idx.push_back('\0');
@@ -90,20 +190,16 @@ int b200h_db_open(const char *data_path, b200h_db **out) {
         IndexEntry e;
         e.key = (uint32_t) f[0]; e.offset = f[1]; e.length = f[2];
         // every entry carries at least its NUL (DBWriter::writeEnd); offset + length must not wrap
-        if (e.length == 0 || e.length > data_size || e.offset > data_size - e.length) { delete db; return db_fail("index entry beyond the data file (or empty) in " + base); }
+        // (a compressed DB's index holds the UNCOMPRESSED length: inflate_db bounds-checks those entries against the frame sizes)
+        if (e.length == 0 || e.offset > data_size || (!compressed && (e.length > data_size || e.offset > data_size - e.length))) { delete db; return db_fail("index entry beyond the data file (or empty) in " + base); }
         db->index.push_back(e);
         p = (*eol == '\n') ? eol + 1 : eol;
     }
-    std::stable_sort(db->index.begin(), db->index.end(), [](const IndexEntry &a, const IndexEntry &b) { return a.key < b.key; });
-    std::vector<char> ty;
-    if (read_file(base + ".dbtype", ty) && ty.size() >= 4) {
-        int32_t v; memcpy(&v, ty.data(), 4);
-        // bit 31 = zstd-compressed entries (DBReader::isCompressed), extended flag 8 = GPU-padded residues (Parameters.h:94): such DBs
-        // need zstd / un-padding, which this reader does not do -- refuse instead of misreading them as text
-        const uint32_t ext = ((uint32_t) v >> 16) & 0x7FFEu;                       // DBReader::getExtendedDbtype
-        if (((uint32_t) v & (1u << 31)) != 0 || (ext & 8u) != 0) { delete db; return db_fail("compressed or GPU-padded DB: not supported by b200h_db_open: " + base); }
-        db->dbtype = v;
+    if (compressed) {
+        std::string err;
+        if (!inflate_db(db->data, db->index, err)) { delete db; return db_fail(err + ": " + base); }
     }
+    std::stable_sort(db->index.begin(), db->index.end(), [](const IndexEntry &a, const IndexEntry &b) { return a.key < b.key; });
     *out = db;
     return B200_OK;
 }

@@ -234,12 +234,13 @@ class Ref:
         return out.raw[:n], int(na.value), int(nacc.value)
 
     # ---- DB triple through the reference's DBWriter / DBReader (ref_glue.cpp) ----
-    def db_write(self, path, dbtype, keys, entries):
+    def db_write(self, path, dbtype, keys, entries, compressed=False):
         keys = np.ascontiguousarray(keys, np.uint32)
         off = np.zeros(len(entries) + 1, np.int64)
         off[1:] = np.cumsum([len(e) for e in entries])
         blob = b"".join(entries) + b"\0"
-        self.lib.ref_db_write(path.encode(), int(dbtype), _p(keys), blob, _p(off), ctypes.c_int64(len(entries)))
+        self.lib.ref_db_write_mode(path.encode(), int(dbtype), _p(keys), blob, _p(off), ctypes.c_int64(len(entries)),
+                                   ctypes.c_int(1 if compressed else 0))
 
     def db_read(self, path, max_entries=1 << 16, cap=1 << 24):
         keys = np.zeros(max_entries, np.uint32); lens = np.zeros(max_entries, np.int64)

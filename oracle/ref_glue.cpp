@@ -698,12 +698,17 @@ int64_t ref_align_query_nucl(const unsigned char *q, int qL, uint32_t qKey, cons
 
 // ---- DB triple: the reference's own DBWriter / DBReader on real files --------------------------------
 // entries i = data[off[i] .. off[i+1]) written under keys[i] in the given order (one writer thread), closed with merge
-void ref_db_write(const char *path, int dbtype, const uint32_t *keys, const char *data, const int64_t *off, int64_t n) {
+// mode: Parameters::WRITER_ASCII_MODE (0) or WRITER_COMPRESSED_MODE (1, zstd frames; createdb --compressed 1)
+void ref_db_write_mode(const char *path, int dbtype, const uint32_t *keys, const char *data, const int64_t *off, int64_t n, int mode) {
     const std::string idx = std::string(path) + ".index";
-    DBWriter w(path, idx.c_str(), 1, 0, dbtype);
+    DBWriter w(path, idx.c_str(), 1, (size_t) mode, dbtype);
     w.open();
     for (int64_t i = 0; i < n; i++) w.writeData(data + off[i], (size_t) (off[i + 1] - off[i]), keys[i], 0);
     w.close(true);
+}
+
+void ref_db_write(const char *path, int dbtype, const uint32_t *keys, const char *data, const int64_t *off, int64_t n) {
+    ref_db_write_mode(path, dbtype, keys, data, off, n, 0);
 }
 
 // reads a DB through DBReader (sorted by key); returns the number of entries; keys/lens (index length) per entry, payloads

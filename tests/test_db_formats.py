@@ -76,6 +76,58 @@ def test_reader_writer_against_live_reference(tmp_path):
     d.close()
 
 
+def _compressed_gold():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "compressed_db_v1.npz"), allow_pickle=False)
+    ents = [bytes(e)[:int(n)] for e, n in zip(g["entries"], g["entry_len"])]
+    return g, ents
+
+
+def test_reader_on_reference_compressed_files(tmp_path):
+    """zstd-compressed DB written by the reference's DBWriter (tests/golden/make_compressed_db_golden.py): entries below 60 bytes
+    are stored raw, the others as one zstd frame each; the reader hands out the plain text and the dbtype without bit 31"""
+    g, ents = _compressed_gold()
+    path = str(tmp_path / "c")
+    for suf, name in (("", "data"), (".index", "index"), (".dbtype", "dbtype")):
+        open(path + suf, "wb").write(g["file_" + name].tobytes())
+    assert int(np.frombuffer(g["file_dbtype"].tobytes(), np.int32)[0]) < 0          # bit 31 set on disk
+    d = db.DB(path)
+    order = np.argsort(g["keys"], kind="stable")
+    assert len(d) == len(ents) and d.dbtype == int(g["reader_dbtype"]) & 0x7fffffff
+    for i, k in enumerate(order):
+        assert d.key(i) == int(g["keys"][k]) and d.data(i) == ents[k] and d.entry_len(i) == len(ents[k]) + 1, i
+    d.close()
+    # a truncated frame and an index length that disagrees with the frame are refused, not misread
+    blob = bytearray(g["file_data"].tobytes())
+    idx = [l.split(b"\t") for l in g["file_index"].tobytes().splitlines()]
+    big = max(idx, key=lambda f: int(f[2]))
+    bad = str(tmp_path / "bad")
+    blob2 = bytearray(blob); blob2[int(big[1]) + 4 + 20] ^= 0x5a
+    open(bad, "wb").write(bytes(blob2)); open(bad + ".index", "wb").write(g["file_index"].tobytes()); open(bad + ".dbtype", "wb").write(g["file_dbtype"].tobytes())
+    with pytest.raises(db.B200Error):
+        db.DB(bad)
+    open(bad, "wb").write(bytes(blob))
+    open(bad + ".index", "wb").write(b"\n".join(b"\t".join([f[0], f[1], str(int(f[2]) + (7 if f is big else 0)).encode()]) for f in idx) + b"\n")
+    with pytest.raises(db.B200Error):
+        db.DB(bad)
+
+
+def test_compressed_reader_against_live_reference(tmp_path):
+    from oracle.pyoracle import Ref
+    if not Ref.available():
+        pytest.skip("oracle/_ref not built here")
+    ref = Ref()
+    rng = np.random.default_rng(9)
+    keys = rng.permutation(5000)[:300].astype(np.uint32)
+    aa = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", np.uint8)
+    ents = [bytes(aa[rng.integers(0, 20, int(rng.integers(0, 900)))]) + b"\n" for _ in keys]
+    ref.db_write(str(tmp_path / "c"), 0, keys, ents, compressed=True)
+    k, l, o, ty = ref.db_read(str(tmp_path / "c"))
+    d = db.DB(str(tmp_path / "c"))
+    assert [d.key(i) for i in range(len(d))] == list(k) and [d.data(i) for i in range(len(d))] == o
+    assert [d.entry_len(i) for i in range(len(d))] == list(l)
+    d.close()
+
+
 @pytest.mark.gpu
 def test_align_module_over_db_files(gold, ctx, submat, tmp_path):
     """query DB + target DB + prefilter DB (ASCII sequences, text records) -> alignment DB: the three output files equal the ones the
