@@ -67,6 +67,28 @@ int b200_prefilter_db(b200_ctx *ctx, const char *query_db, const char *target_db
                       const double *p_back, const char *num2aa, int alphabet, int comp_bias, float comp_bias_scale, int min_diag_score,
                       uint32_t max_res_list_len, uint32_t bucket_queries, uint64_t *n_hits);
 
+/* ---- padded GPU sequence DB: the writer (`mmseqs makepaddedseqdb`, src/util/makepaddedseqdb.cpp:14-153) -------------------------------
+ * Reads the amino-acid DB <src_db> (+ <src_db>_h, plain or compressed) and writes <dst_db>, .index, .dbtype (extended flag
+ * DBTYPE_EXTENDED_GPU), <dst_db>_h (+ .index, .dbtype) and, with write_lookup, <dst_db>.lookup and a copy of <src_db>.source: entries
+ * ordered by ascending length and renumbered 0..n-1, residues as numeric codes (aa2num, Sequence::mapSequence), +32 on the codes the
+ * masker would replace by X (mask_mode 1: tantan repeats with posterior >= mask_prob, runs longer than mask_n_repeats, lower-case
+ * letters if mask_lower_case) or, with mask_mode 0, on lower-case letters; every entry padded with code 20 to a multiple of 4 bytes.
+ * This is the DB b200_db_load_padded / Marv::loadDb read.  likelihood_ratio [alphabet * alphabet] = Qxy / (Px Py), the reference's
+ * ProbabilityMatrix (src/commons/BaseMatrix.h:83-96); may be NULL with mask_mode 0.  The reference's defaults: mask_mode 1,
+ * mask_prob 0.9, mask_lower_case 0, mask_n_repeats 0, write_lookup 1.
+ * The masker's doubles are accumulated in the order of the reference's AVX2 build (what the released x86-64 binaries are); its SSE /
+ * NEON / scalar builds sum in another order and may differ from it -- and from this -- in the last bit of a posterior. */
+int b200h_make_padded_db(const char *src_db, const char *dst_db, const uint8_t aa2num[256], int alphabet, const double *likelihood_ratio,
+                         int mask_mode, double mask_prob, int mask_lower_case, int mask_n_repeats, int write_lookup, int threads);
+/* tantan::getProbabilities as Masker.cpp:22-32 calls it (maxRepeatOffset 50, repeatProb 0.005, repeatEndProb 0.05, decay 0.9, no
+ * indel states): posterior probability of "inside a repeat" per residue.  seq: numeric codes < alphabet. */
+int b200h_tantan_probabilities(const uint8_t *seq, int L, int alphabet, const double *likelihood_ratio, float *probs);
+/* Masker::maskSequence on numeric codes (text = the entry's letters, needed for mask_lower_case; may be NULL otherwise): masked
+ * residues become code alphabet-1 (X).  Returns the number of masked residues, -1 on bad arguments. */
+int b200h_mask_sequence(uint8_t *seq, const char *text, int L, int alphabet, const double *likelihood_ratio, int mask_tantan, double mask_prob,
+                        int mask_lower_case, int mask_n_repeats);
+const char *b200h_paddeddb_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -111,3 +111,46 @@ def prefilter_db(ctx, submat, alphabet, query_db, target_db, prefilter_db_path, 
                                ctypes.c_uint32(bucket_queries), ctypes.byref(nh))
     ctx._check(rc)
     return int(nh.value)
+
+
+def make_padded_db(src_db, dst_db, alphabet, likelihood_ratio=None, mask=1, mask_prob=0.9, mask_lower_case=0, mask_n_repeat=0,
+                   write_lookup=1, threads=0):
+    """`mmseqs makepaddedseqdb` (same parameter names and defaults): the padded GPU sequence DB of an amino-acid DB.
+    likelihood_ratio: [A, A] doubles, the reference's ProbabilityMatrix (needed when mask != 0)."""
+    import os
+    lib = _lib()
+    lib.b200h_paddeddb_last_error.restype = ctypes.c_char_p
+    table = aa2num_table(alphabet)
+    a = alphabet.encode() if isinstance(alphabet, str) else bytes(alphabet)
+    lr = None if likelihood_ratio is None else np.ascontiguousarray(likelihood_ratio, np.float64).reshape(-1)
+    if lr is not None and lr.size != len(a) * len(a):
+        raise ValueError("likelihood_ratio must be [A, A]")
+    if threads <= 0:
+        threads = len(os.sched_getaffinity(0))
+    rc = lib.b200h_make_padded_db(src_db.encode(), dst_db.encode(), _p(table), len(a), None if lr is None else _p(lr), int(mask),
+                                  ctypes.c_double(mask_prob), int(mask_lower_case), int(mask_n_repeat), int(write_lookup), int(threads))
+    if rc != 0:
+        raise B200Error(lib.b200h_paddeddb_last_error().decode())
+
+
+def tantan_probabilities(codes, likelihood_ratio):
+    """posterior probability of "inside a repeat" per residue (tantan as Masker::maskSequence configures it)"""
+    lib = _lib()
+    s = np.ascontiguousarray(codes, np.uint8)
+    lr = np.ascontiguousarray(likelihood_ratio, np.float64)
+    out = np.zeros(len(s), np.float32)
+    if lib.b200h_tantan_probabilities(_p(s), len(s), int(lr.shape[0]), _p(lr), _p(out)) != 0:
+        raise B200Error("b200h_tantan_probabilities: bad arguments")
+    return out
+
+
+def mask_sequence(codes, text, likelihood_ratio, mask_tantan=True, mask_prob=0.9, mask_lower_case=False, mask_n_repeat=0):
+    """Masker::maskSequence on numeric codes -> (masked codes, number of masked residues)"""
+    lib = _lib()
+    s = np.array(codes, np.uint8)
+    lr = np.ascontiguousarray(likelihood_ratio, np.float64)
+    n = lib.b200h_mask_sequence(_p(s), text, len(s), int(lr.shape[0]), _p(lr), 1 if mask_tantan else 0, ctypes.c_double(mask_prob),
+                                1 if mask_lower_case else 0, int(mask_n_repeat))
+    if n < 0:
+        raise B200Error("b200h_mask_sequence: bad arguments")
+    return s, int(n)

@@ -53,6 +53,8 @@
 #include "Debug.h"
 #include "block_aligner.h"
 #include "ksw2.h"
+#include "Masker.h"
+#include "tantan.h"
 
 const char *version = "b200-pinning-harness";   // the reference binary's version string (GpuUtil.cpp:16 uses it in the shm name hash)
 
@@ -783,6 +785,31 @@ void ref_rescore_diagonal(const char *q, int qL, const char *t, int tL, uint16_t
     if (q == NULL) return;
     DistanceCalculator::LocalAlignment r = DistanceCalculator::computeUngappedAlignment(q, (unsigned) qL, t, (unsigned) tL, diagonal, fast.matrix, mode);
     out[0] = r.score; out[1] = r.startPos; out[2] = r.endPos; out[3] = r.diagonalLen; out[4] = r.distToDiagonal; out[5] = r.diagonal;
+}
+
+// ---- repeat masker of makepaddedseqdb (src/commons/Masker.cpp over lib/tantan) ----------------------------------------------------
+// lr: A*A doubles = ProbabilityMatrix (BaseMatrix.h:83-96), the likelihood-ratio matrix tantan is driven with
+void ref_tantan_matrix(double *lr) {
+    static ProbabilityMatrix pm(*g_aa);
+    const int A = g_aa->alphabetSize;
+    for (int i = 0; i < A; i++)
+        for (int j = 0; j < A; j++) lr[i * A + j] = pm.probMatrixPointers[i][j];
+}
+
+// tantan::getProbabilities with the constants of Masker::maskSequence; seq = numeric codes
+void ref_tantan_probabilities(const unsigned char *seq, int L, float *probs) {
+    static ProbabilityMatrix pm(*g_aa);
+    tantan::getProbabilities(seq, seq + L, 50, pm.probMatrixPointers, 0.005, 0.05, 0.9, 0, 0, probs);
+}
+
+// Masker::maskSequence on an ASCII sequence; out = numeric codes after masking (masked residues = code of X); returns the masker's count
+int ref_mask_sequence(const char *ascii, int L, int maskTantan, double maskProb, int maskLowerCase, int maskNrepeats, unsigned char *out) {
+    static Masker masker(*g_aa);
+    Sequence s((size_t) L + 64, Parameters::DBTYPE_AMINO_ACIDS, g_aa, 0, false, false);
+    s.mapSequence(0, 0, ascii, L);
+    const int n = masker.maskSequence(s, maskTantan != 0, maskProb, maskLowerCase != 0, maskNrepeats);
+    memcpy(out, s.numSequence, (size_t) L);
+    return n;
 }
 
 }  // extern "C"
