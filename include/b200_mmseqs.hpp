@@ -6,6 +6,8 @@
 //
 //   b200::Marv               class Marv                      lib/libmarv/src/marv.h:6-58  (scan called at ungappedprefilter.cpp:207)
 //   b200::UngappedAlignment  class UngappedAlignment         src/prefiltering/UngappedAlignment.h:16-34  (QueryMatcher.cpp:119,131)
+//   b200::DiagSubmitQueue    (no counterpart: QueryMatcher owns one UngappedAlignment per OpenMP thread, QueryMatcher.cpp:73 --
+//                            here those threads' align() calls are combined into one device call)
 //   b200::SmithWaterman      class SmithWaterman             src/alignment/StripedSmithWaterman.h:84-222 (Matcher.cpp:51-144)
 //
 // What differs, and why: the device wants many (query,target) pairs per call.  SmithWaterman therefore collects the
@@ -20,6 +22,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -139,11 +143,128 @@ struct __attribute__((__packed__)) CounterResult {  // src/prefiltering/CacheFri
     unsigned char count;
 };
 
+// Many host threads -> one device call (seam B2).  QueryMatcher runs one UngappedAlignment per OpenMP thread and each of
+// them scores its own query's hits; sending those one by one costs a round trip (uploads, launch, download, synchronisation) per
+// query under the context mutex.  The queue combines them: a thread that arrives while no call is in flight becomes the leader of a
+// round -- it takes every request queued so far (its own among them), stages their hit arrays back to back, issues ONE
+// b200_diag_score_batch, hands the results back and wakes the owners; threads that arrive during the call queue up and one of them
+// leads the next round.  No helper thread, no spinning, no added latency for a lone caller (it leads a round of one).
+// Backend: int operator()(const b200_query*, int nq, const uint64_t* hitOffsets, const uint32_t* ids, const uint16_t* diagonals,
+//                         uint8_t* counts, int32_t* raw) -- b200_diag_score_batch on a context, or a stand-in for tests.
+template <typename Backend>
+class DiagSubmitQueueT {
+public:
+    explicit DiagSubmitQueueT(Backend backend, size_t maxQueriesPerCall = 256) : backend_(backend), maxQueries_(std::max<size_t>(1, maxQueriesPerCall)), leader_(false), rounds_(0), requests_(0) {}
+
+    // blocks until the hits of this query are scored; counts in/out as b200_diag_score, raw may be NULL
+    int submit(const b200_query &query, const uint32_t *ids, const uint16_t *diagonals, size_t n, uint8_t *counts, int32_t *raw) {
+        Request req;
+        req.query = query; req.ids = ids; req.diagonals = diagonals; req.counts = counts; req.raw = raw; req.n = n; req.rc = B200_OK; req.done = false;
+        std::unique_lock<std::mutex> lk(mu_);
+        pending_.push_back(&req);
+        requests_++;
+        while (!req.done) {
+            if (leader_) { cv_.wait(lk); continue; }
+            leader_ = true;                                          // this thread leads a round; its own request is still pending
+            std::vector<Request *> batch;
+            const size_t take = std::min(pending_.size(), maxQueries_);
+            batch.assign(pending_.begin(), pending_.begin() + take);
+            pending_.erase(pending_.begin(), pending_.begin() + take);
+            lk.unlock();
+            const int rc = run(batch);
+            lk.lock();
+            for (size_t i = 0; i < batch.size(); i++) { batch[i]->rc = rc; batch[i]->done = true; }
+            rounds_++;
+            leader_ = false;
+            cv_.notify_all();
+        }
+        return req.rc;
+    }
+
+    size_t rounds() const { std::lock_guard<std::mutex> lk(mu_); return rounds_; }        // device calls issued
+    size_t requests() const { std::lock_guard<std::mutex> lk(mu_); return requests_; }    // submit() calls served or queued
+
+private:
+    struct Request {
+        b200_query query;
+        const uint32_t *ids;
+        const uint16_t *diagonals;
+        uint8_t *counts;
+        int32_t *raw;
+        size_t n;
+        int rc;
+        bool done;
+    };
+
+    // only the leader of the current round runs this, so the staging vectors need no lock
+    int run(const std::vector<Request *> &batch) {
+        const size_t nq = batch.size();
+        queries_.resize(nq); offsets_.assign(nq + 1, 0);
+        bool wantRaw = false;
+        for (size_t i = 0; i < nq; i++) {
+            queries_[i] = batch[i]->query;
+            offsets_[i + 1] = offsets_[i] + batch[i]->n;
+            wantRaw = wantRaw || batch[i]->raw != NULL;
+        }
+        const size_t total = (size_t) offsets_[nq];
+        if (total == 0) return B200_OK;
+        ids_.resize(total); diags_.resize(total); counts_.resize(total);
+        if (wantRaw) raw_.resize(total);
+        for (size_t i = 0; i < nq; i++) {
+            const Request &r = *batch[i];
+            if (r.n == 0) continue;
+            memcpy(&ids_[offsets_[i]], r.ids, r.n * sizeof(uint32_t));
+            memcpy(&diags_[offsets_[i]], r.diagonals, r.n * sizeof(uint16_t));
+            memcpy(&counts_[offsets_[i]], r.counts, r.n);
+        }
+        const int rc = backend_(queries_.data(), (int) nq, offsets_.data(), ids_.data(), diags_.data(), counts_.data(), wantRaw ? raw_.data() : NULL);
+        if (rc != B200_OK) return rc;
+        for (size_t i = 0; i < nq; i++) {
+            const Request &r = *batch[i];
+            if (r.n == 0) continue;
+            memcpy(r.counts, &counts_[offsets_[i]], r.n);
+            if (r.raw != NULL) memcpy(r.raw, &raw_[offsets_[i]], r.n * sizeof(int32_t));
+        }
+        return B200_OK;
+    }
+
+    DiagSubmitQueueT(const DiagSubmitQueueT &);
+    DiagSubmitQueueT &operator=(const DiagSubmitQueueT &);
+    Backend backend_;
+    size_t maxQueries_;
+    mutable std::mutex mu_;
+    std::condition_variable cv_;
+    std::vector<Request *> pending_;
+    bool leader_;
+    size_t rounds_, requests_;
+    std::vector<b200_query> queries_;
+    std::vector<uint64_t> offsets_;
+    std::vector<uint32_t> ids_;
+    std::vector<uint16_t> diags_;
+    std::vector<uint8_t> counts_;
+    std::vector<int32_t> raw_;
+};
+
+struct DeviceDiagBackend {       // the product backend: one batched call on the shared context
+    b200_ctx *ctx;
+    int operator()(const b200_query *q, int nq, const uint64_t *off, const uint32_t *ids, const uint16_t *dg, uint8_t *counts, int32_t *raw) const {
+        return b200_diag_score_batch(ctx, q, nq, off, ids, dg, counts, raw);
+    }
+};
+
+class DiagSubmitQueue : public DiagSubmitQueueT<DeviceDiagBackend> {
+public:
+    explicit DiagSubmitQueue(Device *dev, size_t maxQueriesPerCall = 256) : DiagSubmitQueueT<DeviceDiagBackend>(make(dev), maxQueriesPerCall) {}
+private:
+    static DeviceDiagBackend make(Device *dev) { DeviceDiagBackend b; b.ctx = dev->ctx(); return b; }
+};
+
 class UngappedAlignment {
 public:
-    // subMatrix: A*A int16 row-major copy of BaseMatrix::subMatrix; the lookup must already be loaded into `dev`
-    UngappedAlignment(Device *dev, const int16_t *subMatrix, int alphabetSize)
-        : dev_(dev), mat_(subMatrix, subMatrix + (size_t) alphabetSize * alphabetSize), A_(alphabetSize), qlen_(0) {}
+    // subMatrix: A*A int16 row-major copy of BaseMatrix::subMatrix; the lookup must already be loaded into `dev`.
+    // queue (optional): the DiagSubmitQueue shared by the UngappedAlignment objects of all OpenMP threads
+    UngappedAlignment(Device *dev, const int16_t *subMatrix, int alphabetSize, DiagSubmitQueue *queue = NULL)
+        : dev_(dev), queue_(queue), mat_(subMatrix, subMatrix + (size_t) alphabetSize * alphabetSize), A_(alphabetSize), qlen_(0) {}
 
     // createProfile(Sequence*, float* biasCorrection)   UngappedAlignment.cpp:388-421
     int createProfile(const unsigned char *numSequence, int L, const float *biasCorrection) {
@@ -173,11 +294,13 @@ private:
         ids_.resize(n); diags_.resize(n); counts_.resize(n);
         for (size_t i = 0; i < n; i++) { ids_[i] = results[i].id; diags_[i] = results[i].diagonal; counts_[i] = results[i].count; }
         b200_query q; q.profile = profile_.data(); q.qlen = qlen_; q.bias = 0;
-        const int rc = b200_diag_score(dev_->ctx(), &q, ids_.data(), diags_.data(), n, counts_.data(), raw);
+        const int rc = queue_ != NULL ? queue_->submit(q, ids_.data(), diags_.data(), n, counts_.data(), raw)
+                                      : b200_diag_score(dev_->ctx(), &q, ids_.data(), diags_.data(), n, counts_.data(), raw);
         if (rc == B200_OK) for (size_t i = 0; i < n; i++) results[i].count = counts_[i];
         return rc;
     }
     Device *dev_;
+    DiagSubmitQueue *queue_;
     std::vector<int16_t> mat_;
     int A_, qlen_;
     std::vector<int8_t> cb_, profile_;
