@@ -67,6 +67,42 @@ int b200_prefilter_db(b200_ctx *ctx, const char *query_db, const char *target_db
                       const double *p_back, const char *num2aa, int alphabet, int comp_bias, float comp_bias_scale, int min_diag_score,
                       uint32_t max_res_list_len, uint32_t bucket_queries, uint64_t *n_hits);
 
+/* `mmseqs rescorediagonal` on DB files (amino-acid DBs; src/alignment/rescorediagonal.cpp:45-396): every prefilter hit (target key,
+ * diagonal) of every query is rescored on its diagonal by DistanceCalculator::computeUngappedAlignment -- on the device,
+ * b200_rescore_diagonal -- and turned into the reference's records: rescore_mode 0 (HAMMING) "key \t 100*seqId \t diagonal", 1
+ * (SUBSTITUTION) "key \t bitScore \t diagonal", 2-4 (ALIGNMENT / END_TO_END / WINDOW_QUALITY) alignment records with "<alnLen>M" as
+ * backtrace; hits kept when identity, or alnLen, coverage, seqId and E-value pass (:318-327).  Not taken over: --wrapped-scoring and
+ * reverse-strand prefilter DBs (nucleotide), --filter-hits (its precision library).  n_hits / n_records may be NULL. */
+typedef struct b200_rescore_params {
+    int rescore_mode;              /* --rescore-mode, Parameters::RESCORE_MODE_* 0..4 */
+    double eval_thr;               /* -e */
+    float cov_thr;                 /* -c */
+    int cov_mode;                  /* --cov-mode */
+    float seq_id_thr;              /* --min-seq-id */
+    int aln_len_thr;               /* --min-aln-len */
+    int seq_id_mode;               /* --seq-id-mode */
+    int include_identity;          /* --add-self-matches */
+    int add_backtrace;             /* -a */
+    int sort_results;              /* --sort-results */
+} b200_rescore_params;
+int b200_rescorediagonal_db(b200_ctx *ctx, const char *query_db, const char *target_db, const char *prefilter_db, const char *out_db,
+                            const int16_t *sub_matrix, const char *num2aa, int alphabet, const b200_rescore_params *params,
+                            const b200_evalue_params *evalue /* NULL: the ungapped blosum62 set with the target DB's residue count */,
+                            uint32_t bucket_queries, uint64_t *n_hits, uint64_t *n_records);
+/* The host half of the module with the per-hit scorer abstracted (arguments of b200_rescore_diagonal plus the target sequences as the
+ * module staged them: target i = target_data[target_offsets[i] .. target_offsets[i+1])).  Called once with mode = -1 and no hits
+ * ("these are the targets"), then once per bucket of prefilter entries.  b200_rescorediagonal_db passes the device scorer; a test can
+ * pass a checker to exercise the host half alone. */
+typedef int (*b200_rescore_fn)(void *user, const char *query_data, const uint64_t *query_offsets, int n_queries, const uint64_t *hit_offsets,
+                               const uint32_t *ids, const uint16_t *diagonals, const char *target_data, const uint64_t *target_offsets,
+                               uint64_t n_targets, const int8_t *ascii_matrix, int mode, b200_rescore *out);
+int b200h_rescorediagonal_db_with(b200_rescore_fn scorer, void *user, const char *query_db, const char *target_db, const char *prefilter_db,
+                                  const char *out_db, const int16_t *sub_matrix, const char *num2aa, int alphabet, const b200_rescore_params *params,
+                                  const b200_evalue_params *evalue, uint32_t bucket_queries, uint64_t *n_hits, uint64_t *n_records);
+/* SubstitutionMatrix::createAsciiSubMat (SubstitutionMatrix.h:55-72): out [123][123] int8, indexed by the bytes 0..'z' */
+void b200h_ascii_matrix(const int16_t *sub_matrix, const char *num2aa, int alphabet, int nucleotide, int8_t *out);
+const char *b200h_rescore_module_last_error(void);
+
 /* ---- padded GPU sequence DB: the writer (`mmseqs makepaddedseqdb`, src/util/makepaddedseqdb.cpp:14-153) -------------------------------
  * Reads the amino-acid DB <src_db> (+ <src_db>_h, plain or compressed) and writes <dst_db>, .index, .dbtype (extended flag
  * DBTYPE_EXTENDED_GPU), <dst_db>_h (+ .index, .dbtype) and, with write_lookup, <dst_db>.lookup and a copy of <src_db>.source: entries

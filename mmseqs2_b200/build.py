@@ -6,7 +6,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SO = os.path.join(HERE, "libb200align.so")
 SOURCES = [os.path.join(HERE, "csrc", "b200_align.cu"), os.path.join(HERE, "csrc", "b200_nucl.cu"), os.path.join(HERE, "csrc", "b200_backtrace.cu"), os.path.join(HERE, "csrc", "b200_rescore.cu"), os.path.join(HERE, "csrc", "b200_host.cpp"),
-           os.path.join(HERE, "csrc", "b200_alignment.cpp"), os.path.join(HERE, "csrc", "b200_db.cpp"), os.path.join(HERE, "csrc", "b200_gpuserver.cpp"), os.path.join(HERE, "csrc", "b200_multi.cpp"), os.path.join(HERE, "csrc", "b200_paddeddb.cpp")]
+           os.path.join(HERE, "csrc", "b200_alignment.cpp"), os.path.join(HERE, "csrc", "b200_db.cpp"), os.path.join(HERE, "csrc", "b200_gpuserver.cpp"), os.path.join(HERE, "csrc", "b200_multi.cpp"), os.path.join(HERE, "csrc", "b200_paddeddb.cpp"), os.path.join(HERE, "csrc", "b200_rescore_module.cpp")]
 HEADERS = [os.path.join(ROOT, "include", "b200_align.h"), os.path.join(ROOT, "include", "b200_host.h"), os.path.join(HERE, "csrc", "b200_internal.h"),
            os.path.join(ROOT, "include", "b200_alignment.h"), os.path.join(ROOT, "include", "b200_db.h"), os.path.join(ROOT, "include", "b200_gpuserver.h"), os.path.join(ROOT, "include", "b200_multi.h")]
 

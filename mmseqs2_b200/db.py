@@ -154,3 +154,49 @@ def mask_sequence(codes, text, likelihood_ratio, mask_tantan=True, mask_prob=0.9
     if n < 0:
         raise B200Error("b200h_mask_sequence: bad arguments")
     return s, int(n)
+
+
+class RescoreParams(ctypes.Structure):
+    """b200_rescore_params: the rescorediagonal parameters (same meaning and defaults as the module's command line)"""
+    _fields_ = [("rescore_mode", ctypes.c_int), ("eval_thr", ctypes.c_double), ("cov_thr", ctypes.c_float), ("cov_mode", ctypes.c_int),
+                ("seq_id_thr", ctypes.c_float), ("aln_len_thr", ctypes.c_int), ("seq_id_mode", ctypes.c_int), ("include_identity", ctypes.c_int),
+                ("add_backtrace", ctypes.c_int), ("sort_results", ctypes.c_int)]
+
+    def __init__(self, rescore_mode=0, eval_thr=1e-3, cov_thr=0.0, cov_mode=0, seq_id_thr=0.0, aln_len_thr=0, seq_id_mode=0, include_identity=0,
+                 add_backtrace=0, sort_results=0):
+        super().__init__(rescore_mode, eval_thr, cov_thr, cov_mode, seq_id_thr, aln_len_thr, seq_id_mode, include_identity, add_backtrace, sort_results)
+
+
+RESCORE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p)
+
+
+def ascii_matrix(submat, alphabet, nucleotide=False):
+    """SubstitutionMatrix::createAsciiSubMat: [123, 123] int8"""
+    lib = _lib()
+    a = alphabet.encode() if isinstance(alphabet, str) else bytes(alphabet)
+    mat = np.ascontiguousarray(submat.mat, np.int16)
+    out = np.zeros((123, 123), np.int8)
+    lib.b200h_ascii_matrix(_p(mat), a, len(a), 1 if nucleotide else 0, _p(out))
+    return out
+
+
+def rescorediagonal_db(ctx, submat, alphabet, query_db, target_db, prefilter_db, out_db, params, evalue=None, bucket_queries=4096, scorer=None):
+    """`mmseqs rescorediagonal` over DB files -> (hits scored, records written).  scorer: None = the device scorer of ctx; a RESCORE_FN
+    runs the module's host half with that scorer instead (tests/test_rescore_module.py checks the host half this way without a GPU)."""
+    lib = _lib()
+    lib.b200h_rescore_module_last_error.restype = ctypes.c_char_p
+    a = alphabet.encode() if isinstance(alphabet, str) else bytes(alphabet)
+    mat = np.ascontiguousarray(submat.mat, np.int16)
+    nh, nr = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    ev = None if evalue is None else ctypes.byref(evalue)
+    if scorer is None:
+        rc = lib.b200_rescorediagonal_db(ctx.h, query_db.encode(), target_db.encode(), prefilter_db.encode(), out_db.encode(), _p(mat), a, len(a),
+                                         ctypes.byref(params), ev, ctypes.c_uint32(bucket_queries), ctypes.byref(nh), ctypes.byref(nr))
+        ctx._check(rc)
+    else:
+        rc = lib.b200h_rescorediagonal_db_with(scorer, None, query_db.encode(), target_db.encode(), prefilter_db.encode(), out_db.encode(), _p(mat), a,
+                                               len(a), ctypes.byref(params), ev, ctypes.c_uint32(bucket_queries), ctypes.byref(nh), ctypes.byref(nr))
+        if rc != 0:
+            raise B200Error(lib.b200h_rescore_module_last_error().decode())
+    return int(nh.value), int(nr.value)
