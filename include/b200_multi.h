@@ -60,6 +60,15 @@ int b200_multi_align_batch(b200_multi *m, const int16_t *sub_matrix, const doubl
                            const uint32_t *target_keys, const b200_align_params *params, const b200_evalue_params *evalue,
                            b200_result *results, uint32_t *n_results, char *bt_pool, uint64_t bt_cap, uint64_t *n_alignments);
 
+/* ---- the sharding arithmetic on its own (host only, no device) ------------------------------------------------------------------------
+ * bounds[parts + 1]: contiguous ranges of [0, n) balanced by weight -- the query ranges (weights = query lengths) and target slices
+ * (weights = sequence length + 1) of the calls above. */
+void b200h_balanced_ranges(const uint64_t *weights, uint64_t n, int parts, uint64_t *bounds);
+/* One query's per-device top lists (local ids, lists[d][0..counts[d])) -> the global list: ids + first_id[d], (score desc, global id
+ * asc), cut to max_hits.  Returns the number of hits written to out[max_hits]. */
+uint32_t b200h_merge_top_hits(const b200_hit *const *lists, const uint32_t *counts, const uint64_t *first_id, int n_lists, uint32_t max_hits,
+                              b200_hit *out);
+
 #ifdef __cplusplus
 }
 #endif

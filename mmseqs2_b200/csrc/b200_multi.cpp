@@ -38,6 +38,22 @@ std::vector<uint64_t> balanced_ranges(const std::vector<uint64_t> &weight, int p
     return bounds;
 }
 
+// per-device top lists of one query (local ids) -> the global list: ids shifted by the slice's first id, ordered by the deterministic
+// comparator (score desc, global id asc) -- hit_t::compareHitsByScoreAndId -- and cut to max_hits; returns the number written
+uint32_t merge_top_hits(const b200_hit *const *lists, const uint32_t *counts, const uint64_t *first_id, int n_lists, uint32_t max_hits, b200_hit *out) {
+    std::vector<b200_hit> all;
+    for (int d = 0; d < n_lists; d++)
+        for (uint32_t k = 0; k < counts[d]; k++) {
+            b200_hit h = lists[d][k];
+            h.id += (uint32_t) first_id[d];
+            all.push_back(h);
+        }
+    std::sort(all.begin(), all.end(), [](const b200_hit &a, const b200_hit &b) { return a.score != b.score ? a.score > b.score : a.id < b.id; });
+    const uint32_t n = (uint32_t) std::min<size_t>(all.size(), max_hits);
+    if (n > 0) memcpy(out, all.data(), sizeof(b200_hit) * n);
+    return n;
+}
+
 template <typename F>
 int on_every_device(b200_multi *m, F f) {
     const int n = (int) m->ctx.size();
@@ -171,19 +187,11 @@ int b200_multi_ungapped_scan(b200_multi *m, const b200_query *queries, int nq, i
         return b200_ungapped_scan(m->ctx[d], queries, nq, min_score_excl, max_hits, lh[d].data(), ln[d].data(), nullptr);
     });
     if (rc != B200_OK) return rc;
-    std::vector<b200_hit> all;
+    std::vector<const b200_hit *> lists(nd);
+    std::vector<uint32_t> counts(nd);
     for (int q = 0; q < nq; q++) {
-        all.clear();
-        for (int d = 0; d < nd; d++)
-            for (uint32_t k = 0; k < ln[d][q]; k++) {
-                b200_hit h = lh[d][(size_t) q * max_hits + k];
-                h.id += (uint32_t) m->tgt_begin[d];
-                all.push_back(h);
-            }
-        std::sort(all.begin(), all.end(), [](const b200_hit &a, const b200_hit &b) { return a.score != b.score ? a.score > b.score : a.id < b.id; });
-        const uint32_t n = (uint32_t) std::min<size_t>(all.size(), max_hits);
-        if (n > 0) memcpy(hits + (size_t) q * max_hits, all.data(), sizeof(b200_hit) * n);
-        n_hits[q] = n;
+        for (int d = 0; d < nd; d++) { lists[d] = lh[d].data() + (size_t) q * max_hits; counts[d] = ln[d][q]; }
+        n_hits[q] = merge_top_hits(lists.data(), counts.data(), m->tgt_begin.data(), nd, max_hits, hits + (size_t) q * max_hits);
     }
     return B200_OK;
 }
@@ -250,6 +258,17 @@ int b200_multi_align_batch(b200_multi *m, const int16_t *sub_matrix, const doubl
     }
     if (n_alignments) *n_alignments = total_aln;
     return B200_OK;
+}
+
+// ---- the sharding arithmetic on its own (no device): what the multi-device calls cut and merge with; used by the CPU tests ------------
+void b200h_balanced_ranges(const uint64_t *weights, uint64_t n, int parts, uint64_t *bounds) {
+    const std::vector<uint64_t> b = balanced_ranges(std::vector<uint64_t>(weights, weights + n), parts);
+    for (int p = 0; p <= parts; p++) bounds[p] = b[p];
+}
+
+uint32_t b200h_merge_top_hits(const b200_hit *const *lists, const uint32_t *counts, const uint64_t *first_id, int n_lists, uint32_t max_hits,
+                              b200_hit *out) {
+    return merge_top_hits(lists, counts, first_id, n_lists, max_hits, out);
 }
 
 }  // extern "C"
