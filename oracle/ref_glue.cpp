@@ -341,6 +341,13 @@ double ref_evalue(int gapOpen, int gapExtend, int64_t dbResidues, double score, 
     return evaluer.computeEvalue(score, qLen);
 }
 
+// the ungapped parameter set: EvalueComputation(dbResCount, subMat), what rescorediagonal.cpp:107 builds
+double ref_evalue_ungapped(int64_t dbResidues, double score, double qLen, double *bitScore) {
+    EvalueComputation evaluer((size_t) dbResidues, g_aa);
+    if (bitScore != NULL) *bitScore = evaluer.computeBitScore(score);
+    return evaluer.computeEvalue(score, qLen);
+}
+
 // A1: per-diagonal scorer. targets go into a SequenceLookup; hits = (id, diagonal u16); counts out (u8),
 // rescored[i] = UngappedAlignment::scoreSingelSequenceByCounterResult (unclamped).  bias may be NULL.
 void ref_diag_align(const unsigned char *q, int qL, const float *bias, const unsigned char *tdata, const int64_t *toff,

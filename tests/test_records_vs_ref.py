@@ -54,3 +54,11 @@ def test_evalues_and_bit_scores_are_the_reference_doubles():
         bits = ctypes.c_double(0)
         e = ref.lib.ref_evalue(11, 1, ctypes.c_int64(dbres), ctypes.c_double(score), ctypes.c_double(ql), ctypes.byref(bits))
         assert p.evalue(score, ql) == e and p.bit_score(score) == bits.value, (t, dbres, score, ql)
+    # the ungapped set rescorediagonal scores with (EvalueComputation(dbResCount, subMat))
+    ref.lib.ref_evalue_ungapped.restype = ctypes.c_double
+    for t in range(2500):
+        dbres, score, ql = int(10 ** rng.uniform(3, 11)), float(rng.integers(0, 1500)), float(rng.integers(1, 40000))
+        p = al.EvalueParams.defaults("blosum62.out", 0, 0, dbres, gapped=False)
+        bits = ctypes.c_double(0)
+        e = ref.lib.ref_evalue_ungapped(ctypes.c_int64(dbres), ctypes.c_double(score), ctypes.c_double(ql), ctypes.byref(bits))
+        assert p.evalue(score, ql) == e and p.bit_score(score) == bits.value, ("ungapped", t, dbres, score, ql)
