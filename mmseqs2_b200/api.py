@@ -9,6 +9,12 @@ Reference interface            ->  here
   UngappedAlignment::align / scoreSingleSequence                     Context.diag_score()
   SmithWaterman::alignScoreEndPos                                    Context.sw_score_endpos()
   SmithWaterman::ssw_align (modes 0/1)                               Context.sw_align()
+  banded_sw + computerBacktrace (alignment mode 3)                   Context.sw_backtrace()
+  BandedNucleotideAligner::align (ksw_extz2)                         Context.nucl_align()
+  DistanceCalculator::computeUngappedAlignment (rescorediagonal)     Context.load_db_ascii() + Context.rescore_diagonal()
+  Marv over several GPUs (cudasw4 partitions + merge)                MultiContext
+  Alignment::run for a bucket of queries                             mmseqs2_b200.alignment.align_batch()
+  the modules over DB files                                          mmseqs2_b200.db
 """
 import ctypes
 import weakref

@@ -1,5 +1,10 @@
-"""ctypes binding of include/b200_db.h: the DB triple (data / .index / .dbtype) as DBReader / DBWriter define it, the letter mapping
-of Sequence::mapSequence, and the `align` module over DB files (b200_align_db).  Host-side formats; the DPs run in libb200align.so."""
+"""ctypes binding of include/b200_db.h: the DB triple (data / .index / .dbtype, plain or zstd-compressed) as DBReader / DBWriter define
+it, the letter mapping of Sequence::mapSequence, and the reference's modules over DB files:
+
+  mmseqs ungappedprefilter   prefilter_db()          mmseqs align              align_db()
+  mmseqs rescorediagonal     rescorediagonal_db()    mmseqs makepaddedseqdb    make_padded_db()  (host only, with the repeat masker)
+
+Host-side formats; the DPs and scorers run in libb200align.so."""
 import ctypes
 
 import numpy as np
